@@ -61,8 +61,17 @@ struct Arena {
   void release(size_t m) { top = m; }
 };
 
+struct Marker {  // per-stage CUDA-event profiling hook (no-op when null)
+  virtual void mark(const char* name) = 0;
+  virtual ~Marker() {}
+};
+
 struct Ctx {
   cudaStream_t stream = nullptr;
+  Marker* marker = nullptr;
+  void mark(const char* name) {
+    if (marker && !dry) marker->mark(name);
+  }
   Arena arena;
   bool dry = false;         // plan only: no launches
   uint64_t launches = 0;    // kernels launched through this context

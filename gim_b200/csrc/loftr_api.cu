@@ -1,0 +1,659 @@
+// loftr_api.cu - the C ABI of libgimb200 (include/gimb200.h): weight blob -> device model, workspace
+// planning, and the orchestration of one gim_loftr forward (networks/loftr/loftr.py:43-91).
+#include <math.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/gimb200.h"
+#include "ops.cuh"
+
+namespace gimb {
+const char* last_error();
+
+namespace {
+
+struct Conv {
+  const float* w = nullptr;
+  const float* s = nullptr;  // folded BN scale (null: no BN)
+  const float* b = nullptr;
+  int cout = 0, cin = 0, k = 1;
+};
+struct Bottleneck {
+  Conv c1, c2, c3, ds;
+  bool has_ds = false;
+  int stride = 1;
+};
+struct EncLayer {
+  const float *q, *kv, *merge, *mlp0, *mlp2, *n1g, *n1b, *n2g, *n2b;
+};
+
+constexpr int FINE_CHUNK = 16384;  // matches per fine-stage pass
+
+}  // namespace
+}  // namespace gimb
+
+using namespace gimb;
+
+struct gimb_loftr {
+  int device = 0;
+  gimb_loftr_cfg cfg;
+  char* dblob = nullptr;
+  size_t dblob_bytes = 0;
+  std::map<std::string, std::pair<const float*, std::vector<uint32_t>>> tensors;
+  Conv stem;
+  std::vector<Bottleneck> layers[3];
+  Conv l3out, l2out, l2c1, l2c2, l1out, l1c1, l1c2;
+  EncLayer coarse[8], fine[2];
+  std::map<std::pair<int, int>, float*> pe_cache;
+  int64_t* host_count = nullptr;  // pinned
+  uint64_t launches = 0;
+  int sm_count = 148;
+  bool profiling = false;
+  std::vector<std::pair<std::string, float>> last_profile;
+  std::vector<std::string> prof_names;
+};
+
+namespace gimb {
+namespace {
+
+int find(gimb_loftr* m, const std::string& name, const float** out, std::vector<uint32_t>* shape = nullptr) {
+  auto it = m->tensors.find(name);
+  GIMB_CHECK(it != m->tensors.end(), "weight blob: tensor '%s' missing", name.c_str());
+  *out = it->second.first;
+  if (shape) *shape = it->second.second;
+  return 0;
+}
+
+int load_conv(gimb_loftr* m, const std::string& name, bool bn, Conv* c) {
+  std::vector<uint32_t> sh;
+  GIMB_TRY(find(m, name + ".w", &c->w, &sh));
+  GIMB_CHECK(sh.size() == 4 && sh[1] == sh[2], "conv '%s': expected [Cout,k,k,Cin]", name.c_str());
+  c->cout = sh[0]; c->k = sh[1]; c->cin = sh[3];
+  if (bn) {
+    GIMB_TRY(find(m, name + ".s", &c->s));
+    GIMB_TRY(find(m, name + ".b", &c->b));
+  }
+  return 0;
+}
+
+int load_enc(gimb_loftr* m, const std::string& pre, EncLayer* e) {
+  GIMB_TRY(find(m, pre + ".q", &e->q));
+  GIMB_TRY(find(m, pre + ".kv", &e->kv));
+  GIMB_TRY(find(m, pre + ".merge", &e->merge));
+  GIMB_TRY(find(m, pre + ".mlp0", &e->mlp0));
+  GIMB_TRY(find(m, pre + ".mlp2", &e->mlp2));
+  GIMB_TRY(find(m, pre + ".n1g", &e->n1g));
+  GIMB_TRY(find(m, pre + ".n1b", &e->n1b));
+  GIMB_TRY(find(m, pre + ".n2g", &e->n2g));
+  GIMB_TRY(find(m, pre + ".n2b", &e->n2b));
+  return 0;
+}
+
+int build_model(gimb_loftr* m) {
+  GIMB_TRY(load_conv(m, "stem", true, &m->stem));
+  GIMB_CHECK(m->stem.k == 7 && m->stem.cin == 3 && m->stem.cout == 64, "stem must be 7x7 3->64");
+  const int nblk[3] = {3, 4, 6};
+  for (int li = 0; li < 3; ++li) {
+    for (int bi = 0; bi < nblk[li]; ++bi) {
+      Bottleneck b;
+      std::string pre = "l" + std::to_string(li + 1) + "." + std::to_string(bi);
+      GIMB_TRY(load_conv(m, pre + ".c1", true, &b.c1));
+      GIMB_TRY(load_conv(m, pre + ".c2", true, &b.c2));
+      GIMB_TRY(load_conv(m, pre + ".c3", true, &b.c3));
+      b.has_ds = (bi == 0);
+      b.stride = (li > 0 && bi == 0) ? 2 : 1;
+      if (b.has_ds) GIMB_TRY(load_conv(m, pre + ".ds", true, &b.ds));
+      m->layers[li].push_back(b);
+    }
+  }
+  GIMB_TRY(load_conv(m, "fpn.l3out", false, &m->l3out));
+  GIMB_TRY(load_conv(m, "fpn.l2out", false, &m->l2out));
+  GIMB_TRY(load_conv(m, "fpn.l2c1", true, &m->l2c1));
+  GIMB_TRY(load_conv(m, "fpn.l2c2", false, &m->l2c2));
+  GIMB_TRY(load_conv(m, "fpn.l1out", false, &m->l1out));
+  GIMB_TRY(load_conv(m, "fpn.l1c1", true, &m->l1c1));
+  GIMB_TRY(load_conv(m, "fpn.l1c2", false, &m->l1c2));
+  for (int i = 0; i < 8; ++i) GIMB_TRY(load_enc(m, "coarse." + std::to_string(i), &m->coarse[i]));
+  for (int i = 0; i < 2; ++i) GIMB_TRY(load_enc(m, "fine." + std::to_string(i), &m->fine[i]));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+int run_conv(Ctx& ctx, const Conv& c, const float* in, int B, int H, int W, int stride, int act, const float* residual,
+             float* out) {
+  ConvGemm g;
+  g.in = in; g.B = B; g.H = H; g.W = W; g.C1 = c.cin;
+  g.KH = g.KW = c.k; g.stride = stride; g.pad = c.k / 2;
+  g.OH = (H + 2 * g.pad - c.k) / stride + 1;
+  g.OW = (W + 2 * g.pad - c.k) / stride + 1;
+  g.w = c.w; g.Cout = c.cout; g.scale = c.s; g.bias = c.b; g.residual = residual; g.act0 = act; g.out = out;
+  return conv_gemm(ctx, g);
+}
+
+// ResNet trunk + FPN (networks/loftr/backbone/resnet.py:214-235, 306-329).  NCHW in, NHWC out.
+int backbone(Ctx& ctx, gimb_loftr* m, const float* color, int B, int H, int W, float* feat_c, float* feat_f) {
+  Arena& A = ctx.arena;
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
+  const size_t P2 = (size_t)B * H2 * W2, P4 = (size_t)B * H4 * W4, P8 = (size_t)B * H8 * W8;
+  size_t mark = A.mark();
+  float* x1 = A.alloc<float>(P2 * 256);
+  float* x2 = A.alloc<float>(P4 * 512);
+  float* x3 = A.alloc<float>(P8 * 1024);
+  {
+    size_t mk = A.mark();
+    float* x0 = A.alloc<float>(P2 * 64);
+    float* t1 = A.alloc<float>(P2 * 64);
+    float* t2 = A.alloc<float>(P2 * 64);
+    GIMB_CHECK(ctx.dry || !A.overflow, "backbone: workspace exhausted");
+    GIMB_TRY(stem_conv7x7(ctx, color, B, H, W, m->stem.w, m->stem.s, m->stem.b, x0));
+    const float* cur = x0;
+    int cH = H2, cW = W2;
+    float* outs[3] = {x1, x2, x3};
+    for (int li = 0; li < 3; ++li) {
+      float* xo = outs[li];
+      for (size_t bi = 0; bi < m->layers[li].size(); ++bi) {
+        const Bottleneck& b = m->layers[li][bi];
+        const int oH = cH / b.stride, oW = cW / b.stride;
+        // conv1 1x1 + BN + ReLU (at input resolution), conv2 3x3 (stride) + BN + ReLU, conv3 1x1 + BN (+ identity) + ReLU
+        size_t mk2 = A.mark();
+        float* u1 = (li == 0) ? t1 : A.alloc<float>((size_t)B * cH * cW * b.c1.cout);
+        float* u2 = (li == 0) ? t2 : A.alloc<float>((size_t)B * oH * oW * b.c2.cout);
+        GIMB_CHECK(ctx.dry || !A.overflow, "backbone: workspace exhausted");
+        GIMB_TRY(run_conv(ctx, b.c1, cur, B, cH, cW, 1, ACT_RELU, nullptr, u1));
+        GIMB_TRY(run_conv(ctx, b.c2, u1, B, cH, cW, b.stride, ACT_RELU, nullptr, u2));
+        if (b.has_ds) GIMB_TRY(run_conv(ctx, b.ds, cur, B, cH, cW, b.stride, ACT_NONE, nullptr, xo));
+        // identity (xo) is read and overwritten element-wise by the same thread: in-place is safe
+        GIMB_TRY(run_conv(ctx, b.c3, u2, B, oH, oW, 1, ACT_RELU, xo, xo));
+        A.release(mk2);
+        cur = xo; cH = oH; cW = oW;
+      }
+    }
+    A.release(mk);
+  }
+  // FPN
+  GIMB_TRY(run_conv(ctx, m->l3out, x3, B, H8, W8, 1, ACT_NONE, nullptr, feat_c));
+  float* x2s = A.alloc<float>(P4 * 256);
+  float* x2t = A.alloc<float>(P4 * 256);
+  float* x2o = A.alloc<float>(P4 * 196);
+  float* x1s = A.alloc<float>(P2 * 196);
+  float* x1t = A.alloc<float>(P2 * 196);
+  GIMB_CHECK(ctx.dry || !A.overflow, "backbone: workspace exhausted");
+  GIMB_TRY(run_conv(ctx, m->l2out, x2, B, H4, W4, 1, ACT_NONE, nullptr, x2s));
+  GIMB_TRY(upsample2x_add(ctx, feat_c, B, H8, W8, 256, x2s));
+  GIMB_TRY(run_conv(ctx, m->l2c1, x2s, B, H4, W4, 1, ACT_LEAKY, nullptr, x2t));
+  GIMB_TRY(run_conv(ctx, m->l2c2, x2t, B, H4, W4, 1, ACT_NONE, nullptr, x2o));
+  GIMB_TRY(run_conv(ctx, m->l1out, x1, B, H2, W2, 1, ACT_NONE, nullptr, x1s));
+  GIMB_TRY(upsample2x_add(ctx, x2o, B, H4, W4, 196, x1s));
+  GIMB_TRY(run_conv(ctx, m->l1c1, x1s, B, H2, W2, 1, ACT_LEAKY, nullptr, x1t));
+  GIMB_TRY(run_conv(ctx, m->l1c2, x1t, B, H2, W2, 1, ACT_NONE, nullptr, feat_f));
+  A.release(mark);
+  return 0;
+}
+
+int linear(Ctx& ctx, const float* x, const float* x2, int64_t rows, int C1, int C2, const float* w, int cout, int act0,
+           int act1, int split, float div, const uint8_t* row_mask, float* out) {
+  ConvGemm g;
+  g.in = x; g.in2 = x2; g.B = 1; g.H = (int)rows; g.W = 1; g.C1 = C1; g.C2 = C2;
+  g.OH = (int)rows; g.OW = 1;
+  g.w = w; g.Cout = cout; g.act0 = act0; g.act1 = act1; g.act_split = split; g.div = div; g.row_mask = row_mask;
+  g.out = out;
+  return conv_gemm(ctx, g);
+}
+
+// LoFTREncoderLayer.forward (networks/loftr/submodules/transformer.py:35-58); x is updated in place.
+// n sequences; x [n, L, C], src [n, S, C].  fine == true selects the per-match attention kernel.
+int encoder_layer(Ctx& ctx, const EncLayer& e, float* x, const float* src, int64_t n, int L, int S, int C, int nhead,
+                  const uint8_t* xmask, const uint8_t* smask, bool fine) {
+  Arena& A = ctx.arena;
+  size_t mark = A.mark();
+  const int64_t RL = n * L, RS = n * S;
+  float* q = A.alloc<float>((size_t)RL * C);
+  float* kv = A.alloc<float>((size_t)RS * 2 * C);
+  float* msg = A.alloc<float>((size_t)RL * C);
+  float* mrg = A.alloc<float>((size_t)RL * C);
+  float* hid = A.alloc<float>((size_t)RL * 2 * C);
+  GIMB_CHECK(ctx.dry || !A.overflow, "encoder_layer: workspace exhausted");
+  GIMB_TRY(linear(ctx, x, nullptr, RL, C, 0, e.q, C, ACT_ELU1, ACT_ELU1, 1 << 30, 1.f, xmask, q));
+  GIMB_TRY(linear(ctx, src, nullptr, RS, C, 0, e.kv, 2 * C, ACT_ELU1, ACT_DIVS, C, (float)S, smask, kv));
+  if (fine)
+    GIMB_TRY(fine_attention(ctx, q, kv, n, L, C, nhead, msg));
+  else
+    GIMB_TRY(linear_attention(ctx, q, kv, (int)n, L, S, C, nhead, msg));
+  GIMB_TRY(linear(ctx, msg, nullptr, RL, C, 0, e.merge, C, ACT_NONE, ACT_NONE, 1 << 30, 1.f, nullptr, mrg));
+  GIMB_TRY(layernorm(ctx, mrg, e.n1g, e.n1b, nullptr, RL, C, mrg));
+  GIMB_TRY(linear(ctx, x, mrg, RL, C, C, e.mlp0, 2 * C, ACT_RELU, ACT_RELU, 1 << 30, 1.f, nullptr, hid));
+  GIMB_TRY(linear(ctx, hid, nullptr, RL, 2 * C, 0, e.mlp2, C, ACT_NONE, ACT_NONE, 1 << 30, 1.f, nullptr, msg));
+  GIMB_TRY(layernorm(ctx, msg, e.n2g, e.n2b, x, RL, C, x));
+  A.release(mark);
+  return 0;
+}
+
+// LocalFeatureTransformer.forward (transformer.py:80-101): (self, cross) x npairs.  t0 [n,L,C], t1 [n,S,C].
+// When the two token buffers are contiguous and equally shaped the self layers run as one batch of 2n.
+int feature_transformer(Ctx& ctx, const EncLayer* layers, int npairs, float* t0, float* t1, int64_t n, int L, int S,
+                        int C, int nhead, const uint8_t* m0, const uint8_t* m1, bool fine) {
+  const bool batched = (L == S) && (t1 == t0 + (size_t)n * L * C) && (m0 == nullptr || m1 == m0 + n * L);
+  for (int i = 0; i < npairs; ++i) {
+    const EncLayer& self = layers[2 * i];
+    const EncLayer& cross = layers[2 * i + 1];
+    if (batched) {
+      GIMB_TRY(encoder_layer(ctx, self, t0, t0, 2 * n, L, L, C, nhead, m0, m0, fine));
+    } else {
+      GIMB_TRY(encoder_layer(ctx, self, t0, t0, n, L, L, C, nhead, m0, m0, fine));
+      GIMB_TRY(encoder_layer(ctx, self, t1, t1, n, S, S, C, nhead, m1, m1, fine));
+    }
+    GIMB_TRY(encoder_layer(ctx, cross, t0, t1, n, L, S, C, nhead, m0, m1, fine));
+    GIMB_TRY(encoder_layer(ctx, cross, t1, t0, n, S, L, C, nhead, m1, m0, fine));
+  }
+  return 0;
+}
+
+struct Prof : Marker {
+  gimb_loftr* m;
+  cudaStream_t st;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> names;
+  bool on;
+  Prof(gimb_loftr* m_, cudaStream_t s, bool enabled) : m(m_), st(s), on(enabled) {
+    if (on) mark("start");
+  }
+  void mark(const char* name) override {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    names.push_back(name);
+  }
+  void finish() {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    m->last_profile.clear();
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      m->last_profile.push_back({names[i], ms});
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
+
+struct FwdArgs {
+  const float *color0, *color1;
+  const uint8_t *mask0, *mask1;
+  const float *scale0, *scale1;
+  int n, h0, w0, h1, w1;
+  const gimb_loftr_out* out;
+  const gimb_loftr_taps* taps;
+};
+
+int copy_tap(Ctx& ctx, float* dst, const float* src, size_t nfloat) {
+  if (!dst || ctx.dry || nfloat == 0) return 0;
+  GIMB_CUDA(cudaMemcpyAsync(dst, src, nfloat * sizeof(float), cudaMemcpyDeviceToDevice, ctx.stream));
+  return 0;
+}
+
+// the whole forward; in dry mode only the arena is exercised (workspace planning).
+int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
+  Arena& A = ctx.arena;
+  const int n = f.n;
+  const int h0c = f.h0 / 8, w0c = f.w0 / 8, h1c = f.h1 / 8, w1c = f.w1 / 8;
+  const int h0f = f.h0 / 2, w0f = f.w0 / 2, h1f = f.h1 / 2, w1f = f.w1 / 2;
+  const int L = h0c * w0c, S = h1c * w1c;
+  const int C = 256, CF = 128;
+  const bool same = (f.h0 == f.h1 && f.w0 == f.w1);
+  const gimb_loftr_taps notaps = {};
+  const gimb_loftr_taps& taps = f.taps ? *f.taps : notaps;
+  Prof prof(m, ctx.stream, m->profiling && !ctx.dry);
+  ctx.marker = &prof;
+
+  // persistent buffers (bottom of the stack)
+  float* fc0 = A.alloc<float>((size_t)n * L * C);   // FPN coarse maps, later the token buffers
+  float* fc1 = A.alloc<float>((size_t)n * S * C);
+  float* ff0 = A.alloc<float>((size_t)n * h0f * w0f * CF);
+  float* ff1 = A.alloc<float>((size_t)n * h1f * w1f * CF);
+  uint8_t* maskbuf = nullptr;
+  if (f.mask0) maskbuf = A.alloc<uint8_t>((size_t)n * (L + S));
+  GIMB_CHECK(ctx.dry || !A.overflow, "forward: workspace too small");
+
+  // 1. backbone (loftr.py:58-63): one batched pass when both images have the same size
+  if (same) {
+    // cat([color0, color1]) needs a contiguous NCHW batch: stage it unless the caller already provides one
+    const float* both = f.color0;
+    size_t mk = A.mark();
+    const size_t img = (size_t)3 * f.h0 * f.w0;
+    if (ctx.dry || f.color1 != f.color0 + (size_t)n * img) {
+      float* stage = A.alloc<float>(2 * n * img);
+      GIMB_CHECK(ctx.dry || !A.overflow, "forward: workspace too small");
+      if (!ctx.dry) {
+        GIMB_CUDA(cudaMemcpyAsync(stage, f.color0, n * img * sizeof(float), cudaMemcpyDeviceToDevice, ctx.stream));
+        GIMB_CUDA(cudaMemcpyAsync(stage + n * img, f.color1, n * img * sizeof(float), cudaMemcpyDeviceToDevice, ctx.stream));
+      }
+      both = stage;
+    }
+    // fc0/fc1 and ff0/ff1 are contiguous pairs (sizes are multiples of the arena alignment)
+    GIMB_CHECK(ctx.dry || (fc1 == fc0 + (size_t)n * L * C && ff1 == ff0 + (size_t)n * h0f * w0f * CF),
+               "internal: feature buffers not contiguous");
+    GIMB_TRY(backbone(ctx, m, both, 2 * n, f.h0, f.w0, fc0, ff0));
+    A.release(mk);
+  } else {
+    GIMB_TRY(backbone(ctx, m, f.color0, n, f.h0, f.w0, fc0, ff0));
+    GIMB_TRY(backbone(ctx, m, f.color1, n, f.h1, f.w1, fc1, ff1));
+  }
+  prof.mark("backbone");
+  GIMB_TRY(copy_tap(ctx, taps.feat_c_backbone0, fc0, (size_t)n * L * C));
+  GIMB_TRY(copy_tap(ctx, taps.feat_c_backbone1, fc1, (size_t)n * S * C));
+  GIMB_TRY(copy_tap(ctx, taps.feat_f0, ff0, (size_t)n * h0f * w0f * CF));
+  GIMB_TRY(copy_tap(ctx, taps.feat_f1, ff1, (size_t)n * h1f * w1f * CF));
+
+  // 2. positional encoding + coarse transformer (loftr.py:70-80)
+  const float *pe0 = nullptr, *pe1 = nullptr;
+  if (!ctx.dry) {
+    auto i0 = m->pe_cache.find({h0c, w0c}), i1 = m->pe_cache.find({h1c, w1c});
+    GIMB_CHECK(i0 != m->pe_cache.end() && i1 != m->pe_cache.end(),
+               "position-encoding table for %dx%d / %dx%d not set (call gimb_loftr_set_pe)", h0c, w0c, h1c, w1c);
+    pe0 = i0->second; pe1 = i1->second;
+  }
+  GIMB_TRY(add_pe(ctx, fc0, pe0, n, L, C, fc0));
+  GIMB_TRY(add_pe(ctx, fc1, pe1, n, S, C, fc1));
+  const uint8_t *cm0 = nullptr, *cm1 = nullptr;
+  if (f.mask0) {
+    cm0 = maskbuf; cm1 = maskbuf + (size_t)n * L;
+    if (!ctx.dry) {
+      GIMB_CUDA(cudaMemcpyAsync(maskbuf, f.mask0, (size_t)n * L, cudaMemcpyDeviceToDevice, ctx.stream));
+      GIMB_CUDA(cudaMemcpyAsync(maskbuf + (size_t)n * L, f.mask1, (size_t)n * S, cudaMemcpyDeviceToDevice, ctx.stream));
+    }
+  }
+  GIMB_TRY(feature_transformer(ctx, m->coarse, 4, fc0, fc1, n, L, S, C, 8, cm0, cm1, false));
+  prof.mark("coarse_transformer");
+  GIMB_TRY(copy_tap(ctx, taps.feat_c0, fc0, (size_t)n * L * C));
+  GIMB_TRY(copy_tap(ctx, taps.feat_c1, fc1, (size_t)n * S * C));
+
+  // 3. coarse matching (loftr.py:83)
+  const gimb_loftr_out& o = *f.out;
+  int64_t* dcount = A.alloc<int64_t>(1);
+  CoarseMatchArgs cm;
+  cm.f0 = fc0; cm.f1 = fc1; cm.N = n; cm.L = L; cm.S = S; cm.C = C;
+  cm.h0c = h0c; cm.w0c = w0c; cm.h1c = h1c; cm.w1c = w1c; cm.H0 = f.h0; cm.H1 = f.h1;
+  cm.mask0 = cm0; cm.mask1 = cm1; cm.scale0 = f.scale0; cm.scale1 = f.scale1;
+  cm.thr = m->cfg.thr; cm.temperature = m->cfg.dsmax_temperature; cm.border = m->cfg.border_rm;
+  cm.b_ids = o.b_ids; cm.i_ids = o.i_ids; cm.j_ids = o.j_ids;
+  cm.mconf = o.mconf; cm.mkpts0_c = o.mkpts0_c; cm.mkpts1_c = o.mkpts1_c;
+  cm.count = dcount; cm.conf_matrix = taps.conf_matrix;
+  GIMB_TRY(coarse_match(ctx, cm));
+  prof.mark("select_compact");
+
+  // the one host synchronisation of the forward: M sizes the fine stage (reference: torch.where)
+  int64_t M = 0;
+  if (!ctx.dry) {
+    GIMB_CUDA(cudaMemcpyAsync(m->host_count, dcount, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx.stream));
+    GIMB_CUDA(cudaStreamSynchronize(ctx.stream));
+    M = *m->host_count;
+    GIMB_CHECK(M <= o.capacity, "forward: %lld matches exceed the output capacity %lld", (long long)M,
+               (long long)o.capacity);
+  } else {
+    M = std::min<int64_t>((int64_t)n * std::min(L, S), FINE_CHUNK);  // plan for a full chunk
+  }
+  *m_out = M;
+
+  // 4./5. fine level (loftr.py:86-91), in chunks of FINE_CHUNK matches
+  const int Wn = m->cfg.fine_window, WW = Wn * Wn;
+  const int stride = h0f / h0c;
+  for (int64_t m0 = 0; m0 < M; m0 += FINE_CHUNK) {
+    const int64_t mc = std::min<int64_t>(FINE_CHUNK, M - m0);
+    size_t mk = A.mark();
+    float* w0 = A.alloc<float>((size_t)mc * WW * CF);
+    float* w1 = A.alloc<float>((size_t)mc * WW * CF);
+    GIMB_CHECK(ctx.dry || !A.overflow, "forward: workspace too small (fine stage)");
+    GIMB_TRY(fine_gather(ctx, ff0, h0f, w0f, CF, w0c, stride, Wn, o.b_ids, o.i_ids, m0, mc, w0));
+    GIMB_TRY(fine_gather(ctx, ff1, h1f, w1f, CF, w1c, stride, Wn, o.b_ids, o.j_ids, m0, mc, w1));
+    GIMB_TRY(feature_transformer(ctx, m->fine, 1, w0, w1, mc, WW, WW, CF, 8, nullptr, nullptr, true));
+    GIMB_TRY(copy_tap(ctx, taps.fine_win0 ? taps.fine_win0 + (size_t)m0 * WW * CF : nullptr, w0, (size_t)mc * WW * CF));
+    GIMB_TRY(copy_tap(ctx, taps.fine_win1 ? taps.fine_win1 + (size_t)m0 * WW * CF : nullptr, w1, (size_t)mc * WW * CF));
+    FineMatchArgs fm;
+    fm.f0 = w0; fm.f1 = w1; fm.m0 = m0; fm.m = mc; fm.WW = WW; fm.C = CF; fm.Wn = Wn;
+    fm.fscale = (float)f.h0 / (float)h0f;
+    fm.sim_scale = (float)(1.0 / sqrt((double)CF));
+    fm.b_ids = o.b_ids; fm.scale1 = f.scale0 ? f.scale1 : nullptr;
+    fm.mkpts0_c = o.mkpts0_c; fm.mkpts1_c = o.mkpts1_c;
+    fm.mkpts0_f = o.mkpts0_f; fm.mkpts1_f = o.mkpts1_f; fm.expec_f = o.expec_f;
+    GIMB_TRY(fine_match(ctx, fm));
+    A.release(mk);
+  }
+  prof.mark("fine");
+  prof.finish();
+  return 0;
+}
+
+int check_shapes(int n, int h0, int w0, int h1, int w1) {
+  GIMB_CHECK(n >= 1, "batch must be >= 1");
+  GIMB_CHECK(h0 > 0 && w0 > 0 && h1 > 0 && w1 > 0 && h0 % 8 == 0 && w0 % 8 == 0 && h1 % 8 == 0 && w1 % 8 == 0,
+             "image sizes must be positive multiples of 8 (got %dx%d, %dx%d)", h0, w0, h1, w1);
+  return 0;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+}  // namespace gimb
+
+// =================================================================================================
+extern "C" {
+
+const char* gimb_last_error(void) { return gimb::last_error(); }
+int gimb_abi_version(void) { return GIMB_ABI_VERSION; }
+
+int gimb_loftr_create(const void* blob, size_t nbytes, const gimb_loftr_cfg* cfg, int device, gimb_loftr** out) {
+  GIMB_CHECK(blob && out && cfg, "gimb_loftr_create: null argument");
+  GIMB_CHECK(nbytes >= sizeof(gimb_blob_header), "weight blob too small");
+  const gimb_blob_header* hd = (const gimb_blob_header*)blob;
+  GIMB_CHECK(hd->magic == GIMB_BLOB_MAGIC, "weight blob: bad magic");
+  GIMB_CHECK(hd->version == 1, "weight blob: unsupported version %u", hd->version);
+  GIMB_CHECK(hd->total_bytes <= nbytes && hd->data_offset <= hd->total_bytes, "weight blob: truncated");
+  GIMB_CHECK(cfg->fine_window == 5, "only fine_window_size 5 is built (got %d)", cfg->fine_window);
+  int ndev = 0;
+  GIMB_CUDA(cudaGetDeviceCount(&ndev));
+  GIMB_CHECK(device >= 0 && device < ndev, "device %d not available (%d CUDA devices)", device, ndev);
+  GIMB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GIMB_CUDA(cudaGetDeviceProperties(&prop, device));
+  GIMB_CHECK(prop.major == 10, "libgimb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  gimb_loftr* m = new gimb_loftr();
+  m->device = device;
+  m->cfg = *cfg;
+  m->sm_count = prop.multiProcessorCount;
+  const size_t data_bytes = hd->total_bytes - hd->data_offset;
+  m->dblob_bytes = data_bytes;
+  if (cudaMalloc(&m->dblob, data_bytes) != cudaSuccess) {
+    delete m;
+    set_error("cudaMalloc of %zu weight bytes failed", data_bytes);
+    return 1;
+  }
+  cudaMemcpy(m->dblob, (const char*)blob + hd->data_offset, data_bytes, cudaMemcpyHostToDevice);
+  const gimb_blob_entry* ent = (const gimb_blob_entry*)((const char*)blob + sizeof(gimb_blob_header));
+  for (uint32_t i = 0; i < hd->n_entries; ++i) {
+    std::vector<uint32_t> sh(ent[i].shape, ent[i].shape + ent[i].ndim);
+    if (ent[i].offset + ent[i].nbytes > data_bytes) {
+      gimb_loftr_destroy(m);
+      set_error("weight blob: entry %u out of range", i);
+      return 1;
+    }
+    std::string name(ent[i].name, strnlen(ent[i].name, sizeof(ent[i].name)));
+    m->tensors[name] = {(const float*)(m->dblob + ent[i].offset), sh};
+  }
+  if (build_model(m) != 0) {
+    gimb_loftr_destroy(m);
+    return 1;
+  }
+  if (cudaMallocHost(&m->host_count, sizeof(int64_t)) != cudaSuccess) {
+    gimb_loftr_destroy(m);
+    set_error("cudaMallocHost failed");
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+
+void gimb_loftr_destroy(gimb_loftr* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->dblob) cudaFree(h->dblob);
+  for (auto& kv : h->pe_cache) cudaFree(kv.second);
+  if (h->host_count) cudaFreeHost(h->host_count);
+  delete h;
+}
+
+int gimb_loftr_set_pe(gimb_loftr* h, int hc, int wc, const float* host_pe) {
+  GIMB_CHECK(h && host_pe && hc > 0 && wc > 0, "gimb_loftr_set_pe: bad argument");
+  GIMB_CUDA(cudaSetDevice(h->device));
+  auto key = std::make_pair(hc, wc);
+  auto it = h->pe_cache.find(key);
+  float* d = nullptr;
+  if (it != h->pe_cache.end()) {
+    d = it->second;
+  } else {
+    GIMB_CUDA(cudaMalloc(&d, (size_t)hc * wc * 256 * sizeof(float)));
+    h->pe_cache[key] = d;
+  }
+  GIMB_CUDA(cudaMemcpy(d, host_pe, (size_t)hc * wc * 256 * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int gimb_loftr_workspace_bytes(gimb_loftr* h, int n, int h0, int w0, int h1, int w1, size_t* bytes) {
+  GIMB_CHECK(h && bytes, "gimb_loftr_workspace_bytes: null argument");
+  GIMB_TRY(check_shapes(n, h0, w0, h1, w1));
+  Ctx ctx;
+  ctx.dry = true;
+  ctx.arena.dry = true;
+  ctx.sm_count = h->sm_count;
+  gimb_loftr_out o = {};
+  o.capacity = (int64_t)n * std::min((h0 / 8) * (w0 / 8), (h1 / 8) * (w1 / 8));
+  FwdArgs f = {nullptr, nullptr, (const uint8_t*)1, (const uint8_t*)1, nullptr, nullptr, n, h0, w0, h1, w1, &o, nullptr};
+  int64_t M = 0;
+  GIMB_TRY(forward_impl(ctx, h, f, &M));
+  *bytes = ctx.arena.peak + Arena::kAlign;
+  return 0;
+}
+
+int gimb_loftr_forward(gimb_loftr* h, const float* color0, const float* color1, const uint8_t* mask0,
+                       const uint8_t* mask1, const float* scale0, const float* scale1, int n, int h0, int w0, int h1,
+                       int w1, void* workspace, size_t workspace_bytes, const gimb_loftr_out* out,
+                       const gimb_loftr_taps* taps, int64_t* m_out, void* stream) {
+  GIMB_CHECK(h && color0 && color1 && workspace && out && m_out, "gimb_loftr_forward: null argument");
+  GIMB_TRY(check_shapes(n, h0, w0, h1, w1));
+  GIMB_CHECK((mask0 == nullptr) == (mask1 == nullptr), "mask0 and mask1 must be given together");
+  GIMB_CHECK((scale0 == nullptr) == (scale1 == nullptr), "scale0 and scale1 must be given together");
+  const int64_t need = (int64_t)n * std::min((h0 / 8) * (w0 / 8), (h1 / 8) * (w1 / 8));
+  GIMB_CHECK(out->capacity >= need, "output capacity %lld < n*min(L,S) = %lld", (long long)out->capacity, (long long)need);
+  GIMB_CHECK(out->b_ids && out->i_ids && out->j_ids && out->mconf && out->mkpts0_c && out->mkpts1_c && out->mkpts0_f &&
+                 out->mkpts1_f && out->expec_f,
+             "gimb_loftr_out: every output array is required");
+  GIMB_CUDA(cudaSetDevice(h->device));
+  Ctx ctx;
+  ctx.stream = (cudaStream_t)stream;
+  ctx.sm_count = h->sm_count;
+  uintptr_t base = ((uintptr_t)workspace + Arena::kAlign - 1) / Arena::kAlign * Arena::kAlign;
+  ctx.arena.base = (char*)base;
+  ctx.arena.cap = workspace_bytes - (base - (uintptr_t)workspace);
+  FwdArgs f = {color0, color1, mask0, mask1, scale0, scale1, n, h0, w0, h1, w1, out, taps};
+  int rc = forward_impl(ctx, h, f, m_out);
+  h->launches += ctx.launches;
+  return rc;
+}
+
+int gimb_loftr_host_staging_bytes(int n, int h0, int w0, int h1, int w1, int with_mask, int with_scale, size_t* bytes) {
+  GIMB_CHECK(bytes, "null argument");
+  GIMB_TRY(check_shapes(n, h0, w0, h1, w1));
+  size_t b = 0;
+  b += align_up((size_t)n * 3 * h0 * w0 * 4, 256) + align_up((size_t)n * 3 * h1 * w1 * 4, 256);
+  if (with_mask) b += align_up((size_t)n * (h0 / 8) * (w0 / 8), 256) + align_up((size_t)n * (h1 / 8) * (w1 / 8), 256);
+  if (with_scale) b += 2 * align_up((size_t)n * 2 * 4, 256);
+  *bytes = b + 256;
+  return 0;
+}
+
+int gimb_loftr_forward_host(gimb_loftr* h, const float* color0, const float* color1, const uint8_t* mask0,
+                            const uint8_t* mask1, const float* scale0, const float* scale1, int n, int h0, int w0,
+                            int h1, int w1, void* dev_inputs, size_t dev_inputs_bytes, void* workspace,
+                            size_t workspace_bytes, const gimb_loftr_out* dev_out, const gimb_loftr_out* host_out,
+                            int64_t* m_out, uint64_t* h2d_bytes, uint64_t* d2h_bytes, void* stream) {
+  GIMB_CHECK(h && color0 && color1 && dev_inputs && dev_out && host_out && m_out, "gimb_loftr_forward_host: null argument");
+  size_t need = 0;
+  GIMB_TRY(gimb_loftr_host_staging_bytes(n, h0, w0, h1, w1, mask0 != nullptr, scale0 != nullptr, &need));
+  GIMB_CHECK(dev_inputs_bytes >= need, "dev_inputs too small: %zu < %zu", dev_inputs_bytes, need);
+  GIMB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = (char*)(((uintptr_t)dev_inputs + 255) / 256 * 256);
+  uint64_t up = 0;
+  auto push = [&](const void* src, size_t bytes, const void** dst) -> int {
+    GIMB_CUDA(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st));
+    *dst = p;
+    p += align_up(bytes, 256);
+    up += bytes;
+    return 0;
+  };
+  const void *d_c0, *d_c1, *d_m0 = nullptr, *d_m1 = nullptr, *d_s0 = nullptr, *d_s1 = nullptr;
+  GIMB_TRY(push(color0, (size_t)n * 3 * h0 * w0 * 4, &d_c0));
+  GIMB_TRY(push(color1, (size_t)n * 3 * h1 * w1 * 4, &d_c1));
+  if (mask0) {
+    GIMB_TRY(push(mask0, (size_t)n * (h0 / 8) * (w0 / 8), &d_m0));
+    GIMB_TRY(push(mask1, (size_t)n * (h1 / 8) * (w1 / 8), &d_m1));
+  }
+  if (scale0) {
+    GIMB_TRY(push(scale0, (size_t)n * 2 * 4, &d_s0));
+    GIMB_TRY(push(scale1, (size_t)n * 2 * 4, &d_s1));
+  }
+  GIMB_TRY(gimb_loftr_forward(h, (const float*)d_c0, (const float*)d_c1, (const uint8_t*)d_m0, (const uint8_t*)d_m1,
+                              (const float*)d_s0, (const float*)d_s1, n, h0, w0, h1, w1, workspace, workspace_bytes,
+                              dev_out, nullptr, m_out, stream));
+  const int64_t M = *m_out;
+  GIMB_CHECK(M <= host_out->capacity, "host_out capacity %lld < M = %lld", (long long)host_out->capacity, (long long)M);
+  uint64_t down = sizeof(int64_t);
+  auto pull = [&](void* dst, const void* src, size_t bytes) -> int {
+    if (!dst || bytes == 0) return 0;
+    GIMB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    down += bytes;
+    return 0;
+  };
+  GIMB_TRY(pull(host_out->b_ids, dev_out->b_ids, M * 8));
+  GIMB_TRY(pull(host_out->i_ids, dev_out->i_ids, M * 8));
+  GIMB_TRY(pull(host_out->j_ids, dev_out->j_ids, M * 8));
+  GIMB_TRY(pull(host_out->mconf, dev_out->mconf, M * 4));
+  GIMB_TRY(pull(host_out->mkpts0_c, dev_out->mkpts0_c, M * 8));
+  GIMB_TRY(pull(host_out->mkpts1_c, dev_out->mkpts1_c, M * 8));
+  GIMB_TRY(pull(host_out->mkpts0_f, dev_out->mkpts0_f, M * 8));
+  GIMB_TRY(pull(host_out->mkpts1_f, dev_out->mkpts1_f, M * 8));
+  GIMB_TRY(pull(host_out->expec_f, dev_out->expec_f, M * 12));
+  GIMB_CUDA(cudaStreamSynchronize(st));
+  if (h2d_bytes) *h2d_bytes = up;
+  if (d2h_bytes) *d2h_bytes = down;
+  return 0;
+}
+
+uint64_t gimb_loftr_launch_count(gimb_loftr* h) { return h ? h->launches : 0; }
+
+int gimb_loftr_set_profiling(gimb_loftr* h, int enabled) {
+  GIMB_CHECK(h, "null handle");
+  h->profiling = enabled != 0;
+  return 0;
+}
+
+int gimb_loftr_last_profile(gimb_loftr* h, const char** names, float* ms, int* n_stages) {
+  GIMB_CHECK(h && names && ms && n_stages, "null argument");
+  int n = (int)std::min<size_t>(h->last_profile.size(), 32);
+  h->prof_names.resize(n);
+  for (int i = 0; i < n; ++i) {
+    h->prof_names[i] = h->last_profile[i].first;
+    names[i] = h->prof_names[i].c_str();
+    ms[i] = h->last_profile[i].second;
+  }
+  *n_stages = n;
+  return 0;
+}
+
+}  // extern "C"

@@ -87,6 +87,7 @@ struct FineMatchArgs {
   int64_t m0, m;    // chunk offset / size
   int WW, C, Wn;
   float fscale;     // hw0_i[0] / hw0_f[0]
+  float sim_scale;  // 1 / sqrt(C), rounded from double like the reference's python float
   const int64_t* b_ids;
   const float* scale1;  // [N,2] or null (applied iff scale0 is in data, fine_matching.py:68)
   const float* mkpts0_c;

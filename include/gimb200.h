@@ -104,30 +104,34 @@ void gimb_loftr_destroy(gimb_loftr* h);
  * (h, w multiples of 8).  No reference counterpart (PyTorch allocates implicitly). */
 int gimb_loftr_workspace_bytes(gimb_loftr* h, int n, int h0, int w0, int h1, int w1, size_t* bytes);
 
+/* Replaces: the `pe` buffer PositionEncodingSine registers at construction
+ * (networks/loftr/utils/position_encoding.py:22-37, used at loftr.py:74-75).  Uploads and caches the
+ * table for coarse maps of hc x wc cells: host_pe is [hc*wc, 256] fp32, token-major
+ * (pe[(y*wc + x), c] = reference pe[0, c, y, x]).  Must be called once per coarse size before forward. */
+int gimb_loftr_set_pe(gimb_loftr* h, int hc, int wc, const float* host_pe);
+
 /* Replaces: LoFTR.forward(data) (networks/loftr/loftr.py:43-91) for DEVICE inputs.
  *   color0 [n,3,h0,w0], color1 [n,3,h1,w1]  fp32 NCHW RGB in [0,1]   (data['color0'|'color1'])
  *   mask0 [n,h0/8,w0/8], mask1 [n,h1/8,w1/8] uint8 0/1, both NULL or both set (data['mask0'|'mask1'])
  *   scale0, scale1 [n,2] fp32 (w,h) factors, both NULL or both set      (data['scale0'|'scale1'])
- *   pe0 [h0/8*w0/8, 256], pe1 [h1/8*w1/8, 256] fp32: position-encoding tables in token-major
- *     layout (networks/loftr/utils/position_encoding.py:22-43); pe1 may equal pe0.
  *   m_out (host): number of matches M.  */
 int gimb_loftr_forward(gimb_loftr* h, const float* color0, const float* color1,
                        const uint8_t* mask0, const uint8_t* mask1, const float* scale0,
-                       const float* scale1, const float* pe0, const float* pe1, int n, int h0,
-                       int w0, int h1, int w1, void* workspace, size_t workspace_bytes,
-                       const gimb_loftr_out* out, const gimb_loftr_taps* taps, int64_t* m_out,
-                       void* stream);
+                       const float* scale1, int n, int h0, int w0, int h1, int w1, void* workspace,
+                       size_t workspace_bytes, const gimb_loftr_out* out,
+                       const gimb_loftr_taps* taps, int64_t* m_out, void* stream);
 
-/* Same call for HOST buffers (pinned or pageable): inputs are copied host->device, the forward runs,
- * and rows [0, M) of every non-NULL array of `host_out` are copied back (host_out->capacity rows
- * available).  `dev_out` supplies the device staging arrays.  This is the end-to-end entry the
- * ZEB harness / demo.py path maps to (trainer/lightning.py:158-159 moves the batch, runs the model
- * and reads the results back).  *h2d_bytes / *d2h_bytes report the traffic of this call. */
+/* Same call for HOST buffers (pinned or pageable): inputs are copied host->device into `dev_inputs`,
+ * the forward runs, and rows [0, M) of every non-NULL array of `host_out` are copied back
+ * (host_out->capacity rows available).  `dev_out` supplies the device result arrays.  This is the
+ * end-to-end entry the ZEB harness / demo.py path maps to (trainer/lightning.py:158-159 moves the
+ * batch, runs the model; tools/metrics.py:125-130 reads the results back).
+ * *h2d_bytes / *d2h_bytes report the traffic of this call. */
 int gimb_loftr_forward_host(gimb_loftr* h, const float* color0, const float* color1,
                             const uint8_t* mask0, const uint8_t* mask1, const float* scale0,
-                            const float* scale1, const float* pe0, const float* pe1, int n, int h0,
-                            int w0, int h1, int w1, void* dev_inputs, size_t dev_inputs_bytes,
-                            void* workspace, size_t workspace_bytes, const gimb_loftr_out* dev_out,
+                            const float* scale1, int n, int h0, int w0, int h1, int w1,
+                            void* dev_inputs, size_t dev_inputs_bytes, void* workspace,
+                            size_t workspace_bytes, const gimb_loftr_out* dev_out,
                             const gimb_loftr_out* host_out, int64_t* m_out, uint64_t* h2d_bytes,
                             uint64_t* d2h_bytes, void* stream);
 /* Bytes of device staging gimb_loftr_forward_host needs for the inputs (`dev_inputs`). */

@@ -1,0 +1,95 @@
+"""GPU parity: the CUDA path (through the C ABI, via the drop-in module) against
+ (a) golden vectors produced by the unmodified reference, and (b) the CPU oracle run live."""
+import pytest
+import torch
+
+from tests.goldens import CASES, assert_matches_equal, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model():
+    from gim_b200 import LoFTR, get_default_config, load_default_weights
+    m = LoFTR(get_default_config())
+    m.load_state_dict(load_default_weights())
+    return m.eval().cuda()
+
+
+def to_cuda(data):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_golden_parity(model, case):
+    data, gold = load_case(case)
+    d = to_cuda(data)
+    model(d)
+    errs = assert_matches_equal(d, gold, what=case + ": ")
+    print(case, "M =", d["b_ids"].numel(), errs)
+    assert d["mkpts0_f"].dtype == torch.float32 and d["b_ids"].dtype == torch.int64
+    assert d["hw0_c"] == torch.Size((data["color0"].shape[2] // 8, data["color0"].shape[3] // 8))
+
+
+def test_stage_taps_tiny(model):
+    """Stage-level parity on the tiny case: backbone maps, transformer outputs, fine windows."""
+    data, gold = load_case("tiny_64x96")
+    d = to_cuda(data)
+    model(d, taps=["feat_c_backbone0", "feat_c_backbone1", "feat_f0", "feat_f1", "feat_c0", "feat_c1",
+                   "fine_win0", "fine_win1", "conf_matrix"])
+    t = {k: v.cpu() for k, v in d["_taps"].items()}
+    fc = torch.cat([t["feat_c_backbone0"], t["feat_c_backbone1"]], 0).permute(0, 3, 1, 2)
+    ff = torch.cat([t["feat_f0"], t["feat_f1"]], 0).permute(0, 3, 1, 2)
+    e_c = (fc - gold["inter_feat_c_backbone"]).abs().max().item()
+    e_f = (ff - gold["inter_feat_f"]).abs().max().item()
+    e_t0 = (t["feat_c0"] - gold["inter_feat_c0"]).abs().max().item()
+    e_t1 = (t["feat_c1"] - gold["inter_feat_c1"]).abs().max().item()
+    print("backbone c/f err", e_c, e_f, "transformer err", e_t0, e_t1)
+    assert e_c < 1e-4 and e_f < 1e-4
+    assert e_t0 < 2e-4 and e_t1 < 2e-4
+    if gold["b_ids"].numel():
+        e_w0 = (t["fine_win0"] - gold["inter_fine_win0"]).abs().max().item()
+        e_w1 = (t["fine_win1"] - gold["inter_fine_win1"]).abs().max().item()
+        print("fine windows err", e_w0, e_w1)
+        assert e_w0 < 2e-4 and e_w1 < 2e-4
+
+
+def test_conf_matrix_vs_oracle(model):
+    from gim_b200 import load_default_weights
+    from oracle import loftr_oracle
+    data, _ = load_case("tiny_64x96")
+    ref = loftr_oracle.loftr_forward(load_default_weights(), data, return_intermediates=True)
+    d = to_cuda(data)
+    d["return_conf_matrix"] = True
+    model(d)
+    err = (d["conf_matrix"].cpu() - ref["_inter"]["conf_matrix"]).abs().max().item()
+    print("conf_matrix err", err)
+    assert err < 1e-5
+
+
+def test_host_entry_matches_device_entry(model):
+    data, gold = load_case("small_b2_240x320")
+    d = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in data.items()}
+    model(d)  # CPU tensors -> gimb_loftr_forward_host
+    assert d["mkpts1_f"].device.type == "cpu"
+    assert_matches_equal(d, gold, what="host entry: ")
+    assert model.last_h2d_bytes == 2 * data["color0"].numel() * 4
+    assert model.last_d2h_bytes > 0
+
+
+def test_live_oracle_random_pair(model):
+    """A pair that has no committed golden: oracle run live on the GPU box's CPU."""
+    from gim_b200 import load_default_weights, synth
+    from oracle import loftr_oracle
+    c0, c1 = synth.make_pairs(1, 160, 224, first=11)
+    ref = loftr_oracle.loftr_forward(load_default_weights(), dict(color0=c0, color1=c1))
+    d = dict(color0=c0.cuda(), color1=c1.cuda(), image0=c0, image1=c1)
+    model(d)
+    assert_matches_equal(d, {k: ref[k] for k in ("b_ids", "i_ids", "j_ids", "m_bids", "mconf", "mkpts0_c", "mkpts1_c",
+                                                  "mkpts0_f", "mkpts1_f", "expec_f")}, what="live oracle: ")
+
+
+def test_errors_are_loud(model):
+    c = torch.zeros(1, 3, 100, 128, device="cuda")
+    with pytest.raises(RuntimeError):
+        model(dict(color0=c, color1=c, image0=c, image1=c))  # 100 is not a multiple of 8
