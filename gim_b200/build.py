@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgimb200.so")
-SOURCES = ["common.cu", "conv_simt.cu", "transformer.cu", "coarse_match.cu", "fine.cu", "loftr_api.cu"]
+SOURCES = ["common.cu", "conv_simt.cu", "transformer.cu", "coarse_match.cu", "fine.cu", "umma_gemm.cu", "test_hooks.cu", "loftr_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -1,0 +1,91 @@
+// test_hooks.cu - C entry points used only by tests/: run one GEMM-shaped layer through the tcgen05 kernel
+// and through the fp32 CUDA-core kernel on the same device buffers, so the two can be compared with a
+// float64 reference on the host side.
+#include "../../include/gimb200.h"
+#include "ops.cuh"
+#include "umma_gemm.cuh"
+
+using namespace gimb;
+
+namespace {
+__global__ void planes_to_f32_kernel(const __half* hi, const __half* lo, long long rows, int cols, int ld, float* out) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  long long r = idx / cols;
+  int c = (int)(idx - r * cols);
+  out[idx] = __half2float(hi[r * ld + c]) + __half2float(lo[r * ld + c]) * (1.f / kSplitScale);
+}
+}  // namespace
+
+extern "C" int gimb_test_conv(const float* in, const float* in2, int B, int H, int W, int C1, int C2, const float* w, int Cout,
+                              int ksize, int stride, const float* scale, const float* bias, const float* residual,
+                              const uint8_t* row_mask, int act0, int act1, int act_split, float div, float* out_umma,
+                              float* out_umma_planes, float* out_simt, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  GIMB_CHECK(in && w && out_umma && out_simt && workspace, "gimb_test_conv: null argument");
+  Ctx ctx;
+  ctx.stream = (cudaStream_t)stream;
+  int dev = 0;
+  GIMB_CUDA(cudaGetDevice(&dev));
+  GIMB_CUDA(cudaDeviceGetAttribute(&ctx.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  uintptr_t base = ((uintptr_t)workspace + Arena::kAlign - 1) / Arena::kAlign * Arena::kAlign;
+  ctx.arena.base = (char*)base;
+  ctx.arena.cap = workspace_bytes - (base - (uintptr_t)workspace);
+  const int pad = ksize / 2;
+  const int OH = (H + 2 * pad - ksize) / stride + 1, OW = (W + 2 * pad - ksize) / stride + 1;
+  const long long M = (long long)B * OH * OW;
+  const int Cin = C1 + C2;
+
+  // ---- fp32 CUDA-core path
+  ConvGemm c;
+  c.in = in; c.in2 = in2; c.B = B; c.H = H; c.W = W; c.C1 = C1; c.C2 = C2;
+  c.KH = c.KW = ksize; c.stride = stride; c.pad = pad; c.OH = OH; c.OW = OW;
+  c.w = w; c.Cout = Cout; c.scale = scale; c.bias = bias; c.residual = residual; c.row_mask = row_mask;
+  c.act0 = act0; c.act1 = act1; c.act_split = act_split; c.div = div; c.out = out_simt;
+  GIMB_TRY(conv_gemm(ctx, c));
+
+  // ---- tcgen05 path: split the operands, run, optionally re-assemble the output planes
+  auto pitch8 = [](int v) { return (v + 7) / 8 * 8; };
+  Arena& A = ctx.arena;
+  SplitPlanes a, a2, b, o;
+  const long long pix = (long long)B * H * W;
+  a.ld = pitch8(C1);
+  a.hi = A.alloc<__half>(pix * a.ld); a.lo = A.alloc<__half>(pix * a.ld);
+  GIMB_TRY(split_planes(ctx, in, pix, C1, C1, a));
+  if (in2) {
+    a2.ld = pitch8(C2);
+    a2.hi = A.alloc<__half>(pix * a2.ld); a2.lo = A.alloc<__half>(pix * a2.ld);
+    GIMB_TRY(split_planes(ctx, in2, pix, C2, C2, a2));
+  }
+  // weights [Cout][taps][Cin] -> planes with per-tap pitch ldk
+  const int taps = ksize * ksize;
+  const int ldk = pitch8(Cin);
+  b.ld = taps * ldk;
+  b.hi = A.alloc<__half>((size_t)Cout * b.ld); b.lo = A.alloc<__half>((size_t)Cout * b.ld); b.h8 = A.alloc<__half>((size_t)Cout * b.ld);
+  {
+    SplitPlanes bt = b;
+    bt.ld = ldk;  // treat [Cout*taps] rows of Cin -> pitch ldk
+    GIMB_TRY(split_planes(ctx, w, (long long)Cout * taps, Cin, Cin, bt));
+  }
+  o.ld = pitch8(Cout);
+  if (out_umma_planes) { o.hi = A.alloc<__half>(M * o.ld); o.lo = A.alloc<__half>(M * o.ld); }
+  GIMB_CHECK(!A.overflow, "gimb_test_conv: workspace too small");
+
+  UmmaGemm g;
+  g.a = a; g.a2 = a2; g.b = b; g.N = Cout;
+  if (ksize == 1 && stride == 1) {
+    g.mode = 0; g.M = M; g.K1 = C1; g.K2 = C2;
+  } else {
+    g.mode = 1; g.K1 = Cin; g.B = B; g.H = H; g.W = W; g.KH = g.KW = ksize; g.stride = stride; g.pad = pad;
+    g.OH = OH; g.OW = OW; g.ldk = ldk;
+  }
+  g.scale = scale; g.bias = bias; g.residual = residual; g.row_mask = row_mask;
+  g.act0 = act0; g.act1 = act1; g.act_split = act_split; g.div = div;
+  g.out_f32 = out_umma; g.out = o;
+  GIMB_TRY(umma_gemm(ctx, g));
+  if (out_umma_planes) {
+    planes_to_f32_kernel<<<(unsigned)cdiv64(M * Cout, 256), 256, 0, ctx.stream>>>(o.hi, o.lo, M, Cout, o.ld, out_umma_planes);
+    GIMB_LAUNCH_CHECK();
+  }
+  return 0;
+}

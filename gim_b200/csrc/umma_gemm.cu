@@ -1,0 +1,562 @@
+// umma_gemm.cu - tcgen05 (5th-gen tensor core) GEMM / implicit-GEMM convolution with split-fp16 operands.
+//
+// One persistent CTA per SM, warp-specialised (see /opt/skills/guides/blackwell_cuda_programming.md "Anatomy"):
+//   warp 0      TMA producer  : cp.async.bulk.tensor (2-D/3-D row tiles or 4-D NHWC patches, OOB zero fill = conv padding)
+//                               into a ring of SWIZZLE_64B shared-memory stages, mbarrier complete_tx
+//   warp 1      MMA issuer    : one elected lane issues 3 x tcgen05.mma.kind::f16 (M=128, N<=256, K=16) per k16 step
+//                               [A_hi*B_h8 + A_hi*B_lo + A_lo*B_hi] into a double-buffered fp32 TMEM accumulator,
+//                               tcgen05.commit frees smem stages / publishes the accumulator
+//   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns), 2^-8 rescale, folded-BN scale/bias, residual,
+//                               activation, row mask, fp32 store and/or re-split into fp16 planes for the next layer
+//
+// Tile: BM = 128 output rows (mode 0: consecutive rows; mode 1: an 8 x 16 pixel patch of one image),
+//       BN = whole N up to 256 (rounded to 16), BK = 32 fp16 (64-byte rows).
+#include <algorithm>
+
+#include "ops.cuh"
+#include "umma_gemm.cuh"
+
+namespace gimb {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 8 KB
+constexpr int TH = 8, TW = 16;
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COLS = 256;
+
+struct TMaps {
+  CUtensorMap a_hi[4], a_lo[4];  // mode 1 stride 2: four phase views; otherwise index 0
+  CUtensorMap a2_hi, a2_lo;      // mode 0 concat source
+  CUtensorMap b_h8, b_lo, b_hi;
+};
+
+struct KParams {
+  int mode;
+  long long M;
+  int OH, OW, tiles_h, tiles_w, tiles_per_img;
+  int KH, KW, stride, pad;
+  int cb1, cb2, K1;  // k-blocks of a / a2 per tap; channels of a
+  int ldk;
+  int N, n_tiles, bn;
+  int stages, stage_bytes;
+  int num_tiles, num_kb;
+  unsigned idesc;
+  const float* scale;
+  const float* bias;
+  const float* residual;
+  const uint8_t* row_mask;
+  int act0, act1, act_split;
+  float div;
+  float* out_f32;
+  __half* out_hi;
+  __half* out_lo;
+  __half* out_h8;
+  int ldp;
+};
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// A protocol bug would otherwise hang the GPU: after ~2^28 failed polls the kernel traps instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 28)) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout_type [61,64) with SWIZZLE_64B = 4)
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;          // leading byte offset (unused for swizzled K-major; canonical value 1)
+  d |= (uint64_t)(512 >> 4) << 32; // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;          // SWIZZLE_64B
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------- tile decode
+struct TileCoord {
+  int m_tile, n_tile;
+  int img, oh0, ow0;  // mode 1
+};
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
+  TileCoord c;
+  c.m_tile = t / p.n_tiles;
+  c.n_tile = t - c.m_tile * p.n_tiles;
+  c.img = 0; c.oh0 = 0; c.ow0 = 0;
+  if (p.mode == 1) {
+    c.img = c.m_tile / p.tiles_per_img;
+    int r = c.m_tile - c.img * p.tiles_per_img;
+    int th = r / p.tiles_w;
+    c.oh0 = th * TH;
+    c.ow0 = (r - th * p.tiles_w) * TW;
+  }
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ TMaps maps, const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // stage ring, 1024-byte aligned
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bars = base + p.stages * p.stage_bytes;        // barrier block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + p.stages * p.stage_bytes + 256);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
+  auto tfull_bar = [&](int b) { return bars + 128u + 8u * b; };
+  auto tempty_bar = [&](int b) { return bars + 144u + 8u * b; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a_hi[0]);
+    tma_prefetch_desc(&maps.a_lo[0]);
+    tma_prefetch_desc(&maps.b_h8);
+    tma_prefetch_desc(&maps.b_lo);
+    tma_prefetch_desc(&maps.b_hi);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(tfull_bar(b), 1);
+        mbar_init(tempty_bar(b), NUM_EPI_WARPS * 32);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t b_plane = (uint32_t)p.bn * (BK * 2);  // bytes of one B plane tile
+
+  if (warp == 0) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int n0 = tc.n_tile * p.bn;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sA = base + stage * p.stage_bytes;
+          const uint32_t sB = sA + 2 * A_TILE_BYTES;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, (uint32_t)p.stage_bytes);
+          int bk;  // k coordinate into the weight planes
+          if (p.mode == 0) {
+            const int m0 = tc.m_tile * BM;
+            if (kb < p.cb1) {
+              bk = kb * BK;
+              tma_load_3d(sA, &maps.a_hi[0], fb, kb * BK, m0, 0);
+              tma_load_3d(sA + A_TILE_BYTES, &maps.a_lo[0], fb, kb * BK, m0, 0);
+            } else {
+              const int k2 = (kb - p.cb1) * BK;
+              bk = p.K1 + k2;
+              tma_load_3d(sA, &maps.a2_hi, fb, k2, m0, 0);
+              tma_load_3d(sA + A_TILE_BYTES, &maps.a2_lo, fb, k2, m0, 0);
+            }
+          } else {
+            const int tap = kb / p.cb1, cb = kb - tap * p.cb1;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            int dh = kh - p.pad, dw = kw - p.pad, view = 0;
+            if (p.stride == 2) {
+              const int py = dh & 1, px = dw & 1;
+              view = py * 2 + px;
+              dh = (dh - py) / 2;
+              dw = (dw - px) / 2;
+            }
+            bk = tap * p.ldk + cb * BK;
+            tma_load_4d(sA, &maps.a_hi[view], fb, cb * BK, tc.ow0 + dw, tc.oh0 + dh, tc.img);
+            tma_load_4d(sA + A_TILE_BYTES, &maps.a_lo[view], fb, cb * BK, tc.ow0 + dw, tc.oh0 + dh, tc.img);
+          }
+          tma_load_3d(sB, &maps.b_h8, fb, bk, n0, 0);
+          tma_load_3d(sB + b_plane, &maps.b_lo, fb, bk, n0, 0);
+          tma_load_3d(sB + 2 * b_plane, &maps.b_hi, fb, bk, n0, 0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++local) {
+        const int buf = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(tempty_bar(buf), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * ACC_COLS;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = base + stage * p.stage_bytes;
+          const uint32_t sB = sA + 2 * A_TILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint32_t koff = kk * 32;  // 16 fp16 = 32 bytes inside the 64-byte swizzle row
+            const uint64_t a_hi = make_desc_sw64(sA + koff);
+            const uint64_t a_lo = make_desc_sw64(sA + A_TILE_BYTES + koff);
+            const uint64_t b_h8 = make_desc_sw64(sB + koff);
+            const uint64_t b_lo = make_desc_sw64(sB + b_plane + koff);
+            const uint64_t b_hi = make_desc_sw64(sB + 2 * b_plane + koff);
+            umma_f16(tacc, a_hi, b_h8, p.idesc, (kb | kk) != 0);
+            umma_f16(tacc, a_hi, b_lo, p.idesc, 1);
+            umma_f16(tacc, a_lo, b_hi, p.idesc, 1);
+          }
+          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(buf));      // accumulator complete
+      }
+    }
+  } else {
+    // =============================================================== epilogue warps
+    const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int r_in_tile = q * 32 + lane;  // accumulator row owned by this thread
+    int local = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      const TileCoord tc = decode_tile(p, t);
+      const int n0 = tc.n_tile * p.bn;
+      long long row;
+      bool row_ok;
+      if (p.mode == 0) {
+        row = (long long)tc.m_tile * BM + r_in_tile;
+        row_ok = row < p.M;
+      } else {
+        const int oh = tc.oh0 + r_in_tile / TW, ow = tc.ow0 + r_in_tile % TW;
+        row_ok = oh < p.OH && ow < p.OW;
+        row = ((long long)tc.img * p.OH + oh) * p.OW + ow;
+      }
+      float rmask = 1.f;
+      if (p.row_mask && row_ok) rmask = (float)p.row_mask[row];
+      mbar_wait(tfull_bar(buf), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        uint32_t raw32[32];
+        tmem_ld32(taddr + c0, raw32);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw32[j]) * (1.f / kSplitScale);
+        const int cbase = n0 + c0;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int co = cbase + j4 * 4;
+          if (co >= p.N) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = 0.f;
+            continue;
+          }
+          if (p.scale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + co));
+            const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+            v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], sc.x, bi.x);
+            v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], sc.y, bi.y);
+            v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], sc.z, bi.z);
+            v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], sc.w, bi.w);
+          }
+          if (p.residual) {
+            const float4 rr = *reinterpret_cast<const float4*>(p.residual + row * p.N + co);
+            v[j4 * 4 + 0] += rr.x; v[j4 * 4 + 1] += rr.y; v[j4 * 4 + 2] += rr.z; v[j4 * 4 + 3] += rr.w;
+          }
+          const int act = co >= p.act_split ? p.act1 : p.act0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = apply_act(v[j4 * 4 + e], act, p.div) * rmask;
+          if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + row * p.N + co) =
+              make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+        if (p.out_hi) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int co = cbase + j8 * 8;
+            if (co >= p.ldp) continue;
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+            __align__(16) __half h8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float x = v[j8 * 8 + e];
+              const __half h = __float2half_rn(x);
+              const float hf = __half2float(h);
+              hi[e] = h;
+              lo[e] = __float2half_rn((x - hf) * kSplitScale);
+              h8[e] = __float2half_rn(hf * kSplitScale);
+            }
+            *reinterpret_cast<uint4*>(p.out_hi + row * p.ldp + co) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(p.out_lo + row * p.ldp + co) = *reinterpret_cast<const uint4*>(lo);
+            if (p.out_h8) *reinterpret_cast<uint4*>(p.out_h8 + row * p.ldp + co) = *reinterpret_cast<const uint4*>(h8);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------- fp32 -> planes
+__global__ void split_planes_kernel(const float* __restrict__ src, long long rows, int cols, int src_ld, __half* hi,
+                                    __half* lo, __half* h8, int ld) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = rows * ld;
+  if (idx >= total) return;
+  long long r = idx / ld;
+  int c = (int)(idx - r * ld);
+  float x = c < cols ? src[r * src_ld + c] : 0.f;
+  __half h = __float2half_rn(x);
+  float hf = __half2float(h);
+  hi[idx] = h;
+  lo[idx] = __float2half_rn((x - hf) * kSplitScale);
+  if (h8) h8[idx] = __float2half_rn(hf * kSplitScale);
+}
+
+// ------------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GIMB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+    GIMB_CHECK(f && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    fn = (EncodeTiledFn)f;
+  }
+  *out = fn;
+  return 0;
+}
+
+// fp16 tensor map, SWIZZLE_64B, inner box = 32 elements (64 B).  dims/strides innermost first; strides in BYTES for
+// dims 1.. (rank-1 entries).
+int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+             const uint32_t* box) {
+  EncodeTiledFn enc;
+  GIMB_TRY(get_encode(&enc));
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  GIMB_CHECK(((uintptr_t)ptr & 15) == 0, "tensor map: base address not 16-byte aligned");
+  for (int i = 0; i + 1 < rank; ++i) GIMB_CHECK(gs[i] % 16 == 0, "tensor map: stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GIMB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rank %d, dims %llu %llu %llu)", (int)r, rank,
+             (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)(rank > 2 ? gd[2] : 0));
+  return 0;
+}
+
+int rows_map(CUtensorMap* m, const __half* ptr, uint64_t K, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  uint64_t dims[3] = {K, rows, 1};
+  uint64_t strides[2] = {ld * 2, rows * ld * 2};
+  uint32_t box[3] = {BK, box_rows, 1};
+  return make_map(m, ptr, 3, dims, strides, box);
+}
+
+}  // namespace
+
+int split_planes(Ctx& ctx, const float* src, int64_t rows, int cols, int src_ld, const SplitPlanes& dst) {
+  GIMB_CHECK(dst.ld % 8 == 0 && dst.ld >= cols, "split_planes: plane pitch must be a multiple of 8 and >= cols");
+  if (ctx.dry || rows == 0) return 0;
+  long long total = rows * dst.ld;
+  split_planes_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, ctx.stream>>>(src, rows, cols, src_ld, dst.hi, dst.lo, dst.h8, dst.ld);
+  ctx.launches++;
+  GIMB_LAUNCH_CHECK();
+  return 0;
+}
+
+int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
+  GIMB_CHECK(g.a.hi && g.a.lo && g.b.hi && g.b.lo && g.b.h8, "umma_gemm: operand planes missing");
+  GIMB_CHECK(g.N >= 8 && g.N % 4 == 0, "umma_gemm: N must be a multiple of 4");
+  GIMB_CHECK(g.a.ld % 8 == 0 && g.b.ld % 8 == 0, "umma_gemm: plane pitches must be multiples of 8");
+  GIMB_CHECK(g.stride == 1 || g.stride == 2, "umma_gemm: stride 1 or 2");
+  GIMB_CHECK((g.scale == nullptr) == (g.bias == nullptr), "umma_gemm: scale and bias go together");
+  GIMB_CHECK(g.out_f32 || g.out.hi, "umma_gemm: no output requested");
+  if (g.out.hi) GIMB_CHECK(g.out.lo && g.out.ld % 8 == 0 && g.out.ld >= g.N && g.out.ld - g.N < 32, "umma_gemm: bad output planes");
+  if (ctx.dry) return 0;
+
+  KParams p = {};
+  TMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.mode = g.mode;
+  p.N = g.N;
+  p.n_tiles = cdiv(g.N, 256);
+  p.bn = cdiv(cdiv(g.N, p.n_tiles), 16) * 16;
+  p.KH = g.KH; p.KW = g.KW; p.stride = g.stride; p.pad = g.pad;
+  p.K1 = g.K1;
+  p.cb1 = cdiv(g.K1, BK);
+  p.cb2 = 0;
+  int m_tiles;
+  if (g.mode == 0) {
+    GIMB_CHECK(g.M > 0, "umma_gemm: M must be positive");
+    p.M = g.M;
+    m_tiles = (int)cdiv64(g.M, BM);
+    GIMB_TRY(rows_map(&maps.a_hi[0], g.a.hi, g.K1, g.M, g.a.ld, BM));
+    GIMB_TRY(rows_map(&maps.a_lo[0], g.a.lo, g.K1, g.M, g.a.ld, BM));
+    if (g.K2 > 0) {
+      GIMB_CHECK(g.a2.hi && g.a2.lo, "umma_gemm: concat planes missing");
+      p.cb2 = cdiv(g.K2, BK);
+      GIMB_TRY(rows_map(&maps.a2_hi, g.a2.hi, g.K2, g.M, g.a2.ld, BM));
+      GIMB_TRY(rows_map(&maps.a2_lo, g.a2.lo, g.K2, g.M, g.a2.ld, BM));
+    }
+    p.num_kb = p.cb1 + p.cb2;
+    p.ldk = 0;
+    const uint64_t Kw = (uint64_t)g.K1 + g.K2;
+    GIMB_CHECK((uint64_t)g.b.ld >= Kw, "umma_gemm: weight pitch smaller than K");
+    GIMB_TRY(rows_map(&maps.b_h8, g.b.h8, Kw, g.N, g.b.ld, p.bn));
+    GIMB_TRY(rows_map(&maps.b_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn));
+    GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn));
+  } else {
+    GIMB_CHECK(g.K2 == 0, "umma_gemm: concat only in row mode");
+    GIMB_CHECK(g.stride == 1 || (g.H % 2 == 0 && g.W % 2 == 0), "umma_gemm: stride-2 needs even H, W");
+    p.OH = g.OH; p.OW = g.OW;
+    p.tiles_h = cdiv(g.OH, TH); p.tiles_w = cdiv(g.OW, TW);
+    p.tiles_per_img = p.tiles_h * p.tiles_w;
+    m_tiles = g.B * p.tiles_per_img;
+    p.M = (long long)g.B * g.OH * g.OW;
+    p.num_kb = g.KH * g.KW * p.cb1;
+    p.ldk = g.ldk;
+    GIMB_CHECK(g.ldk >= g.K1 && g.ldk % 8 == 0, "umma_gemm: bad per-tap weight pitch");
+    const uint64_t ld = g.a.ld;
+    const int nviews = g.stride == 2 ? 4 : 1;
+    for (int v = 0; v < nviews; ++v) {
+      const int py = v >> 1, px = v & 1;
+      const uint64_t s = g.stride;
+      uint64_t dims[4] = {(uint64_t)g.K1, (uint64_t)g.W / s, (uint64_t)g.H / s, (uint64_t)g.B};
+      uint64_t strides[3] = {s * ld * 2, s * (uint64_t)g.W * ld * 2, (uint64_t)g.H * g.W * ld * 2};
+      uint32_t box[4] = {BK, TW, TH, 1};
+      const size_t off = ((size_t)py * g.W + px) * ld;
+      GIMB_TRY(make_map(&maps.a_hi[v], g.a.hi + off, 4, dims, strides, box));
+      GIMB_TRY(make_map(&maps.a_lo[v], g.a.lo + off, 4, dims, strides, box));
+    }
+    const uint64_t Kw = (uint64_t)g.KH * g.KW * g.ldk;
+    GIMB_CHECK((uint64_t)g.b.ld >= Kw, "umma_gemm: weight pitch smaller than K");
+    GIMB_TRY(rows_map(&maps.b_h8, g.b.h8, Kw, g.N, g.b.ld, p.bn));
+    GIMB_TRY(rows_map(&maps.b_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn));
+    GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn));
+  }
+  p.stage_bytes = 2 * A_TILE_BYTES + 3 * p.bn * BK * 2;
+  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
+  p.stages = std::max(1, std::min(p.stages, std::max(2, p.num_kb)));
+  p.num_tiles = m_tiles * p.n_tiles;
+  p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+  p.scale = g.scale; p.bias = g.bias; p.residual = g.residual; p.row_mask = g.row_mask;
+  p.act0 = g.act0; p.act1 = g.act1; p.act_split = g.act_split; p.div = g.div;
+  p.out_f32 = g.out_f32; p.out_hi = g.out.hi; p.out_lo = g.out.lo; p.out_h8 = g.out.h8; p.ldp = g.out.ld;
+
+  const int smem = p.stages * p.stage_bytes + 1024 + 512;
+  static bool attr_done = false;
+  if (!attr_done) {
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_done = true;
+  }
+  const int grid = std::min(p.num_tiles, ctx.sm_count);
+  umma_gemm_kernel<<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+  ctx.launches++;
+  GIMB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace gimb

@@ -1,0 +1,57 @@
+// umma_gemm.cuh - host-side description of the tcgen05 split-fp16 GEMM / implicit-GEMM convolution.
+//
+//   D[M, N] = epi( A[M, K] * B[N, K]^T )        fp32-equivalent product on the 5th-gen tensor cores
+//
+// Operand format ("split fp16"): every fp32 value x is carried as two fp16 planes
+//   hi = fp16(x),  lo = fp16((x - hi) * 2^8)
+// and the B operand additionally as h8 = 2^8 * hi (exact).  One fp32 TMEM accumulator receives
+//   D' = A_hi * B_h8  +  A_hi * B_lo  +  A_lo * B_hi      (3 x tcgen05.mma kind::f16 per k16 step)
+// so that D = 2^-8 * D' = A*B up to the dropped lo*lo term (2^-22 relative) - the precision class the
+// survey validated against the fp32 reference ("3 MMAs at the f16 rate").
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace gimb {
+
+constexpr float kSplitScale = 256.f;  // 2^8
+
+struct SplitPlanes {        // an fp32 tensor carried as fp16 planes, channel (K) stride `ld` elements
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  __half* h8 = nullptr;     // only for tensors used as the B operand
+  int ld = 0;               // row pitch in elements (multiple of 8)
+};
+
+struct UmmaGemm {
+  // ---- A operand
+  // mode 0 (rows):  A is [M, K1] (+ optional concat [M, K2]) row-major planes
+  // mode 1 (conv):  A is NHWC [B, H, W, Cin] planes; output pixel tiles are TH x TW patches
+  int mode = 0;
+  SplitPlanes a, a2;
+  int64_t M = 0;          // rows (mode 0)
+  int K1 = 0, K2 = 0;     // mode 0: channels of a / a2 ; mode 1: K1 = Cin
+  int B = 1, H = 1, W = 1, KH = 1, KW = 1, stride = 1, pad = 0, OH = 1, OW = 1;
+  // ---- B operand: planes [N, Kw] with Kw = KH*KW*ldk (per-tap pitch ldk >= Cin, multiple of 8)
+  SplitPlanes b;
+  int N = 0;
+  int ldk = 0;            // per-tap K pitch of the weight planes (mode 1); mode 0: unused
+  // ---- epilogue:  v = acc * 2^-8 ; v = v*scale+bias ; v += residual ; v = act(v) ; v *= row_mask
+  const float* scale = nullptr;
+  const float* bias = nullptr;
+  const float* residual = nullptr;   // [M, N] fp32, pitch N
+  const uint8_t* row_mask = nullptr;
+  int act0 = ACT_NONE, act1 = ACT_NONE, act_split = 1 << 30;
+  float div = 1.f;
+  float* out_f32 = nullptr;          // [M, N] pitch N (optional)
+  SplitPlanes out;                   // optional fp16 planes (hi, lo[, h8]); pad channels [N, ld) are zeroed
+};
+
+int umma_gemm(Ctx& ctx, const UmmaGemm& g);
+
+// fp32 -> split planes (weights at load time; test helper)
+int split_planes(Ctx& ctx, const float* src, int64_t rows, int cols, int src_ld, const SplitPlanes& dst);
+
+}  // namespace gimb
