@@ -9,6 +9,7 @@
 
 #include "ops.cuh"
 #include "simt_tile.cuh"
+#include "split.cuh"
 
 namespace gimb {
 
@@ -66,7 +67,8 @@ constexpr int ST_PH = ST_TH * 2 + 5, ST_PW = ST_TW * 2 + 5;  // 21 x 69
 
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in, int B, int H, int W,
                                                    const float* __restrict__ w, const float* __restrict__ scale,
-                                                   const float* __restrict__ bias, float* __restrict__ out) {
+                                                   const float* __restrict__ bias, float* __restrict__ out,
+                                                   const PlanesDev sp) {
   extern __shared__ __align__(16) float st_smem[];
   float (*wsm)[64] = reinterpret_cast<float (*)[64]>(st_smem);                       // [tap*3+ci][co]
   float (*patch)[ST_PH][ST_PW + 1] = reinterpret_cast<float (*)[ST_PH][ST_PW + 1]>(st_smem + 147 * 64);  // [3]
@@ -112,7 +114,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in,
     }
   int oh = oh0 + py, ow = ow0 + px;
   if (oh < OH && ow < OW) {
-    float4* o = reinterpret_cast<float4*>(out + (((size_t)b * OH + oh) * OW + ow) * 64);
+    const size_t pix = ((size_t)b * OH + oh) * OW + ow;
+    float4* o = reinterpret_cast<float4*>(out + pix * 64);
 #pragma unroll
     for (int c4 = 0; c4 < 16; ++c4) {
       float4 r;
@@ -120,7 +123,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in,
       r.y = fmaxf(fmaf(acc[c4 * 4 + 1], scale[c4 * 4 + 1], bias[c4 * 4 + 1]), 0.f);
       r.z = fmaxf(fmaf(acc[c4 * 4 + 2], scale[c4 * 4 + 2], bias[c4 * 4 + 2]), 0.f);
       r.w = fmaxf(fmaf(acc[c4 * 4 + 3], scale[c4 * 4 + 3], bias[c4 * 4 + 3]), 0.f);
-      o[c4] = r;
+      if (out) o[c4] = r;
+      if (sp.hi) split4_store(sp, pix * sp.ld + c4 * 4, r.x, r.y, r.z, r.w);
     }
   }
 }
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in,
 // --------------------------------------------------------------------------- bilinear 2x + add
 // F.interpolate(scale_factor=2, mode='bilinear', align_corners=True): src = dst * (in-1)/(out-1).
 __global__ void upsample2x_add_kernel(const float* __restrict__ low, int B, int h, int w, int C4,
-                                      float* __restrict__ out, float ry, float rx) {
+                                      float* __restrict__ out, float ry, float rx, const PlanesDev sp) {
   const int OH = 2 * h, OW = 2 * w;
   size_t total = (size_t)B * OH * OW * C4;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
@@ -154,16 +158,29 @@ __global__ void upsample2x_add_kernel(const float* __restrict__ low, int B, int 
     r.y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
     r.z += hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
     r.w += hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-    *o = r;
+    if (sp.hi) {
+      split4_store(sp, pix * sp.ld + c * 4, r.x, r.y, r.z, r.w);
+      // zero the pad channels [C, ld) once per pixel
+      if (c == C4 - 1)
+        for (int z = C4 * 4; z < sp.ld; z += 4) split4_store(sp, pix * sp.ld + z, 0.f, 0.f, 0.f, 0.f);
+    } else {
+      *o = r;
+    }
   }
 }
 
 __global__ void add_pe_kernel(const float4* __restrict__ feat, const float4* __restrict__ pe, size_t total,
-                              size_t per_image, float4* __restrict__ out) {
+                              size_t per_image, float4* __restrict__ out, const PlanesDev sp, int C4) {
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     float4 a = feat[idx], b = pe[idx % per_image];
-    out[idx] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    float4 r = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    out[idx] = r;
+    if (sp.hi) {
+      size_t row = idx / C4;
+      int c = (int)(idx - row * C4);
+      split4_store(sp, row * sp.ld + c * 4, r.x, r.y, r.z, r.w);
+    }
   }
 }
 
@@ -201,8 +218,9 @@ int conv_gemm(Ctx& ctx, const ConvGemm& c) {
 }
 
 int stem_conv7x7(Ctx& ctx, const float* in_nchw, int B, int H, int W, const float* w, const float* scale,
-                 const float* bias, float* out_nhwc) {
+                 const float* bias, float* out_nhwc, const SplitPlanes* planes) {
   if (ctx.dry) return 0;
+  const PlanesDev sp = planes ? dev(*planes) : PlanesDev{nullptr, nullptr, nullptr, 0};
   dim3 grid(cdiv(W / 2, ST_TW), cdiv(H / 2, ST_TH), B);
   const int smem = (147 * 64 + 3 * ST_PH * (ST_PW + 1)) * (int)sizeof(float);
   static bool attr_done = false;
@@ -210,31 +228,34 @@ int stem_conv7x7(Ctx& ctx, const float* in_nchw, int B, int H, int W, const floa
     GIMB_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  stem_kernel<<<grid, 256, smem, ctx.stream>>>(in_nchw, B, H, W, w, scale, bias, out_nhwc);
+  stem_kernel<<<grid, 256, smem, ctx.stream>>>(in_nchw, B, H, W, w, scale, bias, out_nhwc, sp);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;
 }
 
-int upsample2x_add(Ctx& ctx, const float* low, int B, int h, int w, int C, float* out) {
+int upsample2x_add(Ctx& ctx, const float* low, int B, int h, int w, int C, float* out, const SplitPlanes* planes) {
   GIMB_CHECK(C % 4 == 0, "upsample2x_add: C %% 4 != 0");
   if (ctx.dry) return 0;
+  const PlanesDev sp = planes ? dev(*planes) : PlanesDev{nullptr, nullptr, nullptr, 0};
+  GIMB_CHECK(!planes || (planes->ld % 4 == 0 && planes->ld >= C), "upsample2x_add: bad plane pitch");
   float ry = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
   float rx = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
   size_t total = (size_t)B * 4 * h * w * (C / 4);
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx.sm_count * 16);
-  upsample2x_add_kernel<<<blocks, 256, 0, ctx.stream>>>(low, B, h, w, C / 4, out, ry, rx);
+  upsample2x_add_kernel<<<blocks, 256, 0, ctx.stream>>>(low, B, h, w, C / 4, out, ry, rx, sp);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;
 }
 
-int add_pe(Ctx& ctx, const float* feat, const float* pe, int B, int L, int C, float* tokens) {
+int add_pe(Ctx& ctx, const float* feat, const float* pe, int B, int L, int C, float* tokens, const SplitPlanes* planes) {
   GIMB_CHECK(C % 4 == 0, "add_pe: C %% 4 != 0");
   if (ctx.dry) return 0;
+  const PlanesDev sp = planes ? dev(*planes) : PlanesDev{nullptr, nullptr, nullptr, 0};
   size_t per = (size_t)L * C / 4, total = per * B;
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx.sm_count * 16);
-  add_pe_kernel<<<blocks, 256, 0, ctx.stream>>>((const float4*)feat, (const float4*)pe, total, per, (float4*)tokens);
+  add_pe_kernel<<<blocks, 256, 0, ctx.stream>>>((const float4*)feat, (const float4*)pe, total, per, (float4*)tokens, sp, C / 4);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;

@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "ops.cuh"
+#include "split.cuh"
 
 namespace gimb {
 namespace {
@@ -13,7 +14,7 @@ namespace {
 __global__ void __launch_bounds__(256) fine_gather_kernel(const float* __restrict__ feat, int hf, int wf, int C4,
                                                           int wc, int stride, int Wn, const int64_t* __restrict__ b_ids,
                                                           const int64_t* __restrict__ ids, int64_t m0, int64_t m,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, const PlanesDev sp) {
   const int WW = Wn * Wn, pad = Wn / 2;
   const int per_match = WW * C4;
   for (int64_t mm = blockIdx.x; mm < m; mm += gridDim.x) {
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(256) fine_gather_kernel(const float* __restric
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (y >= 0 && y < hf && x >= 0 && x < wf) v = base[((size_t)y * wf + x) * C4 + c];
       o[e] = v;
+      if (sp.hi) split4_store(sp, ((size_t)mm * WW + t) * sp.ld + c * 4, v.x, v.y, v.z, v.w);
     }
   }
 }
@@ -99,11 +101,12 @@ __global__ void __launch_bounds__(256) fine_match_kernel(const FineMatchArgs a) 
 }  // namespace
 
 int fine_gather(Ctx& ctx, const float* feat_f, int hf, int wf, int C, int wc, int stride, int Wn,
-                const int64_t* b_ids, const int64_t* ids, int64_t m0, int64_t m, float* out) {
+                const int64_t* b_ids, const int64_t* ids, int64_t m0, int64_t m, float* out, const SplitPlanes* planes) {
   GIMB_CHECK(C % 4 == 0, "fine_gather: C %% 4 != 0");
   if (ctx.dry || m == 0) return 0;
+  const PlanesDev sp = planes ? dev(*planes) : PlanesDev{nullptr, nullptr, nullptr, 0};
   int blocks = (int)std::min<int64_t>(m, (int64_t)ctx.sm_count * 32);
-  fine_gather_kernel<<<blocks, 256, 0, ctx.stream>>>(feat_f, hf, wf, C / 4, wc, stride, Wn, b_ids, ids, m0, m, out);
+  fine_gather_kernel<<<blocks, 256, 0, ctx.stream>>>(feat_f, hf, wf, C / 4, wc, stride, Wn, b_ids, ids, m0, m, out, sp);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;

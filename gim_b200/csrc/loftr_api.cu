@@ -1,6 +1,7 @@
 // loftr_api.cu - the C ABI of libgimb200 (include/gimb200.h): weight blob -> device model, workspace
 // planning, and the orchestration of one gim_loftr forward (networks/loftr/loftr.py:43-91).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -16,8 +17,16 @@ const char* last_error();
 
 namespace {
 
+enum Engine : int { ENGINE_SIMT = 0, ENGINE_TC = 1 };
+
+// weights of one GEMM-shaped layer in both engine formats
+struct Wt {
+  const float* w = nullptr;   // fp32 [cout][k*k*cin]            (CUDA-core engine)
+  SplitPlanes wp;             // fp16 planes [cout][k*k*ldk]      (tcgen05 engine)
+  int ldk = 0;                // per-tap K pitch of the planes
+};
 struct Conv {
-  const float* w = nullptr;
+  Wt wt;
   const float* s = nullptr;  // folded BN scale (null: no BN)
   const float* b = nullptr;
   int cout = 0, cin = 0, k = 1;
@@ -28,10 +37,13 @@ struct Bottleneck {
   int stride = 1;
 };
 struct EncLayer {
-  const float *q, *kv, *merge, *mlp0, *mlp2, *n1g, *n1b, *n2g, *n2b;
+  Wt q, kv, merge, mlp0, mlp2;
+  const float *n1g, *n1b, *n2g, *n2b;
 };
 
 constexpr int FINE_CHUNK = 16384;  // matches per fine-stage pass
+
+inline int pitch8(int c) { return (c + 7) / 8 * 8; }
 
 }  // namespace
 }  // namespace gimb
@@ -40,9 +52,12 @@ using namespace gimb;
 
 struct gimb_loftr {
   int device = 0;
+  int engine = ENGINE_TC;
   gimb_loftr_cfg cfg;
   char* dblob = nullptr;
   size_t dblob_bytes = 0;
+  char* dplanes = nullptr;     // fp16 weight planes of every GEMM layer
+  size_t dplanes_bytes = 0, dplanes_top = 0;
   std::map<std::string, std::pair<const float*, std::vector<uint32_t>>> tensors;
   Conv stem;
   std::vector<Bottleneck> layers[3];
@@ -68,24 +83,52 @@ int find(gimb_loftr* m, const std::string& name, const float** out, std::vector<
   return 0;
 }
 
-int load_conv(gimb_loftr* m, const std::string& name, bool bn, Conv* c) {
+// carve fp16 planes (h8, lo, hi) for a weight [rows = cout*taps][cin] out of m->dplanes and fill them.
+// With m->dplanes == nullptr only the size is accumulated (first pass).
+int make_weight_planes(gimb_loftr* m, Ctx& ctx, Wt* wt, int cout, int taps, int cin) {
+  wt->ldk = pitch8(cin);
+  const size_t n = (size_t)cout * taps * wt->ldk;
+  __half* ptr[3];
+  for (int i = 0; i < 3; ++i) {
+    m->dplanes_top = (m->dplanes_top + 255) / 256 * 256;
+    ptr[i] = m->dplanes ? (__half*)(m->dplanes + m->dplanes_top) : nullptr;
+    m->dplanes_top += n * sizeof(__half);
+  }
+  if (!m->dplanes) return 0;
+  wt->wp.h8 = ptr[0]; wt->wp.lo = ptr[1]; wt->wp.hi = ptr[2];
+  SplitPlanes tap_view = wt->wp;
+  tap_view.ld = wt->ldk;  // rows of cin values, pitch ldk
+  GIMB_TRY(split_planes(ctx, wt->w, (int64_t)cout * taps, cin, cin, tap_view));
+  wt->wp.ld = taps * wt->ldk;
+  return 0;
+}
+
+int load_conv(gimb_loftr* m, Ctx& ctx, const std::string& name, bool bn, Conv* c) {
   std::vector<uint32_t> sh;
-  GIMB_TRY(find(m, name + ".w", &c->w, &sh));
+  GIMB_TRY(find(m, name + ".w", &c->wt.w, &sh));
   GIMB_CHECK(sh.size() == 4 && sh[1] == sh[2], "conv '%s': expected [Cout,k,k,Cin]", name.c_str());
   c->cout = sh[0]; c->k = sh[1]; c->cin = sh[3];
   if (bn) {
     GIMB_TRY(find(m, name + ".s", &c->s));
     GIMB_TRY(find(m, name + ".b", &c->b));
   }
+  if (c->cin % 4 == 0) GIMB_TRY(make_weight_planes(m, ctx, &c->wt, c->cout, c->k * c->k, c->cin));
   return 0;
 }
 
-int load_enc(gimb_loftr* m, const std::string& pre, EncLayer* e) {
-  GIMB_TRY(find(m, pre + ".q", &e->q));
-  GIMB_TRY(find(m, pre + ".kv", &e->kv));
-  GIMB_TRY(find(m, pre + ".merge", &e->merge));
-  GIMB_TRY(find(m, pre + ".mlp0", &e->mlp0));
-  GIMB_TRY(find(m, pre + ".mlp2", &e->mlp2));
+int load_linear(gimb_loftr* m, Ctx& ctx, const std::string& name, Wt* wt) {
+  std::vector<uint32_t> sh;
+  GIMB_TRY(find(m, name, &wt->w, &sh));
+  GIMB_CHECK(sh.size() == 2, "linear '%s': expected [out,in]", name.c_str());
+  return make_weight_planes(m, ctx, wt, sh[0], 1, sh[1]);
+}
+
+int load_enc(gimb_loftr* m, Ctx& ctx, const std::string& pre, EncLayer* e) {
+  GIMB_TRY(load_linear(m, ctx, pre + ".q", &e->q));
+  GIMB_TRY(load_linear(m, ctx, pre + ".kv", &e->kv));
+  GIMB_TRY(load_linear(m, ctx, pre + ".merge", &e->merge));
+  GIMB_TRY(load_linear(m, ctx, pre + ".mlp0", &e->mlp0));
+  GIMB_TRY(load_linear(m, ctx, pre + ".mlp2", &e->mlp2));
   GIMB_TRY(find(m, pre + ".n1g", &e->n1g));
   GIMB_TRY(find(m, pre + ".n1b", &e->n1b));
   GIMB_TRY(find(m, pre + ".n2g", &e->n2g));
@@ -93,81 +136,157 @@ int load_enc(gimb_loftr* m, const std::string& pre, EncLayer* e) {
   return 0;
 }
 
-int build_model(gimb_loftr* m) {
-  GIMB_TRY(load_conv(m, "stem", true, &m->stem));
+int build_model(gimb_loftr* m, Ctx& ctx) {
+  for (int li = 0; li < 3; ++li) m->layers[li].clear();
+  GIMB_TRY(load_conv(m, ctx, "stem", true, &m->stem));
   GIMB_CHECK(m->stem.k == 7 && m->stem.cin == 3 && m->stem.cout == 64, "stem must be 7x7 3->64");
   const int nblk[3] = {3, 4, 6};
   for (int li = 0; li < 3; ++li) {
     for (int bi = 0; bi < nblk[li]; ++bi) {
       Bottleneck b;
       std::string pre = "l" + std::to_string(li + 1) + "." + std::to_string(bi);
-      GIMB_TRY(load_conv(m, pre + ".c1", true, &b.c1));
-      GIMB_TRY(load_conv(m, pre + ".c2", true, &b.c2));
-      GIMB_TRY(load_conv(m, pre + ".c3", true, &b.c3));
+      GIMB_TRY(load_conv(m, ctx, pre + ".c1", true, &b.c1));
+      GIMB_TRY(load_conv(m, ctx, pre + ".c2", true, &b.c2));
+      GIMB_TRY(load_conv(m, ctx, pre + ".c3", true, &b.c3));
       b.has_ds = (bi == 0);
       b.stride = (li > 0 && bi == 0) ? 2 : 1;
-      if (b.has_ds) GIMB_TRY(load_conv(m, pre + ".ds", true, &b.ds));
+      if (b.has_ds) GIMB_TRY(load_conv(m, ctx, pre + ".ds", true, &b.ds));
       m->layers[li].push_back(b);
     }
   }
-  GIMB_TRY(load_conv(m, "fpn.l3out", false, &m->l3out));
-  GIMB_TRY(load_conv(m, "fpn.l2out", false, &m->l2out));
-  GIMB_TRY(load_conv(m, "fpn.l2c1", true, &m->l2c1));
-  GIMB_TRY(load_conv(m, "fpn.l2c2", false, &m->l2c2));
-  GIMB_TRY(load_conv(m, "fpn.l1out", false, &m->l1out));
-  GIMB_TRY(load_conv(m, "fpn.l1c1", true, &m->l1c1));
-  GIMB_TRY(load_conv(m, "fpn.l1c2", false, &m->l1c2));
-  for (int i = 0; i < 8; ++i) GIMB_TRY(load_enc(m, "coarse." + std::to_string(i), &m->coarse[i]));
-  for (int i = 0; i < 2; ++i) GIMB_TRY(load_enc(m, "fine." + std::to_string(i), &m->fine[i]));
+  GIMB_TRY(load_conv(m, ctx, "fpn.l3out", false, &m->l3out));
+  GIMB_TRY(load_conv(m, ctx, "fpn.l2out", false, &m->l2out));
+  GIMB_TRY(load_conv(m, ctx, "fpn.l2c1", true, &m->l2c1));
+  GIMB_TRY(load_conv(m, ctx, "fpn.l2c2", false, &m->l2c2));
+  GIMB_TRY(load_conv(m, ctx, "fpn.l1out", false, &m->l1out));
+  GIMB_TRY(load_conv(m, ctx, "fpn.l1c1", true, &m->l1c1));
+  GIMB_TRY(load_conv(m, ctx, "fpn.l1c2", false, &m->l1c2));
+  for (int i = 0; i < 8; ++i) GIMB_TRY(load_enc(m, ctx, "coarse." + std::to_string(i), &m->coarse[i]));
+  for (int i = 0; i < 2; ++i) GIMB_TRY(load_enc(m, ctx, "fine." + std::to_string(i), &m->fine[i]));
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-int run_conv(Ctx& ctx, const Conv& c, const float* in, int B, int H, int W, int stride, int act, const float* residual,
-             float* out) {
-  ConvGemm g;
-  g.in = in; g.B = B; g.H = H; g.W = W; g.C1 = c.cin;
-  g.KH = g.KW = c.k; g.stride = stride; g.pad = c.k / 2;
-  g.OH = (H + 2 * g.pad - c.k) / stride + 1;
-  g.OW = (W + 2 * g.pad - c.k) / stride + 1;
-  g.w = c.w; g.Cout = c.cout; g.scale = c.s; g.bias = c.b; g.residual = residual; g.act0 = act; g.out = out;
-  return conv_gemm(ctx, g);
+// An activation tensor [rows, C]: fp32 (pitch C) and/or split fp16 planes (pitch pitch8(C)).
+struct ActT {
+  float* f32 = nullptr;
+  SplitPlanes sp;
+  int C = 0;
+  const SplitPlanes* planes() const { return sp.hi ? &sp : nullptr; }
+};
+
+struct Fwd {  // per-forward context
+  Ctx& ctx;
+  gimb_loftr* m;
+  bool tc() const { return m->engine == ENGINE_TC; }
+  // Allocate an activation.  SIMT engine: always fp32 only.  TC engine: as requested.
+  ActT alloc(size_t rows, int C, bool want_f32, bool want_split, bool want_h8 = false) {
+    ActT a;
+    a.C = C;
+    if (!tc()) { want_f32 = true; want_split = false; }
+    if (want_f32) a.f32 = ctx.arena.alloc<float>(rows * C);
+    if (want_split) {
+      a.sp.ld = pitch8(C);
+      a.sp.hi = ctx.arena.alloc<__half>(rows * a.sp.ld);
+      a.sp.lo = ctx.arena.alloc<__half>(rows * a.sp.ld);
+      if (want_h8) a.sp.h8 = ctx.arena.alloc<__half>(rows * a.sp.ld);
+    }
+    return a;
+  }
+};
+
+ActT view_rows(const ActT& a, size_t row0) {
+  ActT v = a;
+  if (a.f32) v.f32 = a.f32 + row0 * a.C;
+  if (a.sp.hi) {
+    v.sp.hi = a.sp.hi + row0 * a.sp.ld;
+    v.sp.lo = a.sp.lo + row0 * a.sp.ld;
+    if (a.sp.h8) v.sp.h8 = a.sp.h8 + row0 * a.sp.ld;
+  }
+  return v;
 }
 
-// ResNet trunk + FPN (networks/loftr/backbone/resnet.py:214-235, 306-329).  NCHW in, NHWC out.
-int backbone(Ctx& ctx, gimb_loftr* m, const float* color, int B, int H, int W, float* feat_c, float* feat_f) {
+struct Epi {
+  const float* scale = nullptr;
+  const float* bias = nullptr;
+  const float* residual = nullptr;
+  const uint8_t* row_mask = nullptr;
+  int act0 = ACT_NONE, act1 = ACT_NONE, act_split = 1 << 30;
+  float div = 1.f;
+};
+
+// one GEMM-shaped layer on the selected engine.  in2: channel concat (1x1 only).
+int gemm(Fwd& F, const Wt& wt, int cin1, int cin2, int cout, int k, int stride, const ActT& in, const ActT* in2, int B,
+         int H, int W, const Epi& e, const ActT& out) {
+  const int pad = k / 2;
+  const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+  if (!F.tc()) {
+    ConvGemm g;
+    g.in = in.f32; g.in2 = in2 ? in2->f32 : nullptr;
+    g.B = B; g.H = H; g.W = W; g.C1 = cin1; g.C2 = cin2;
+    g.KH = g.KW = k; g.stride = stride; g.pad = pad; g.OH = OH; g.OW = OW;
+    g.w = wt.w; g.Cout = cout; g.scale = e.scale; g.bias = e.bias; g.residual = e.residual; g.row_mask = e.row_mask;
+    g.act0 = e.act0; g.act1 = e.act1; g.act_split = e.act_split; g.div = e.div; g.out = out.f32;
+    return conv_gemm(F.ctx, g);
+  }
+  UmmaGemm g;
+  g.a = in.sp;
+  if (in2) g.a2 = in2->sp;
+  g.b = wt.wp; g.N = cout;
+  if (k == 1 && stride == 1) {
+    g.mode = 0; g.M = (int64_t)B * H * W; g.K1 = cin1; g.K2 = cin2;
+  } else {
+    g.mode = 1; g.K1 = cin1; g.B = B; g.H = H; g.W = W; g.KH = g.KW = k; g.stride = stride; g.pad = pad;
+    g.OH = OH; g.OW = OW; g.ldk = wt.ldk;
+  }
+  g.scale = e.scale; g.bias = e.bias; g.residual = e.residual; g.row_mask = e.row_mask;
+  g.act0 = e.act0; g.act1 = e.act1; g.act_split = e.act_split; g.div = e.div;
+  g.out_f32 = out.f32; g.out = out.sp;
+  return umma_gemm(F.ctx, g);
+}
+
+int run_conv(Fwd& F, const Conv& c, const ActT& in, int B, int H, int W, int stride, int act, const float* residual,
+             const ActT& out) {
+  Epi e;
+  e.scale = c.s; e.bias = c.b; e.residual = residual; e.act0 = e.act1 = act;
+  return gemm(F, c.wt, c.cin, 0, c.cout, c.k, stride, in, nullptr, B, H, W, e, out);
+}
+
+// ResNet trunk + FPN (networks/loftr/backbone/resnet.py:214-235, 306-329).  NCHW in; feat_c / feat_f are fp32 NHWC.
+int backbone(Fwd& F, const float* color, int B, int H, int W, float* feat_c, float* feat_f) {
+  Ctx& ctx = F.ctx;
+  gimb_loftr* m = F.m;
   Arena& A = ctx.arena;
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
   const size_t P2 = (size_t)B * H2 * W2, P4 = (size_t)B * H4 * W4, P8 = (size_t)B * H8 * W8;
   size_t mark = A.mark();
-  float* x1 = A.alloc<float>(P2 * 256);
-  float* x2 = A.alloc<float>(P4 * 512);
-  float* x3 = A.alloc<float>(P8 * 1024);
+  // block outputs: fp32 (identity path) + split planes (next GEMM operand)
+  ActT xs[3] = {F.alloc(P2, 256, true, true), F.alloc(P4, 512, true, true), F.alloc(P8, 1024, true, true)};
   {
     size_t mk = A.mark();
-    float* x0 = A.alloc<float>(P2 * 64);
-    float* t1 = A.alloc<float>(P2 * 64);
-    float* t2 = A.alloc<float>(P2 * 64);
+    ActT x0 = F.alloc(P2, 64, false, true);
     GIMB_CHECK(ctx.dry || !A.overflow, "backbone: workspace exhausted");
-    GIMB_TRY(stem_conv7x7(ctx, color, B, H, W, m->stem.w, m->stem.s, m->stem.b, x0));
-    const float* cur = x0;
+    GIMB_TRY(stem_conv7x7(ctx, color, B, H, W, m->stem.wt.w, m->stem.s, m->stem.b, x0.f32, x0.planes()));
+    ActT cur = x0;
     int cH = H2, cW = W2;
-    float* outs[3] = {x1, x2, x3};
     for (int li = 0; li < 3; ++li) {
-      float* xo = outs[li];
+      ActT& xo = xs[li];
       for (size_t bi = 0; bi < m->layers[li].size(); ++bi) {
         const Bottleneck& b = m->layers[li][bi];
         const int oH = cH / b.stride, oW = cW / b.stride;
-        // conv1 1x1 + BN + ReLU (at input resolution), conv2 3x3 (stride) + BN + ReLU, conv3 1x1 + BN (+ identity) + ReLU
         size_t mk2 = A.mark();
-        float* u1 = (li == 0) ? t1 : A.alloc<float>((size_t)B * cH * cW * b.c1.cout);
-        float* u2 = (li == 0) ? t2 : A.alloc<float>((size_t)B * oH * oW * b.c2.cout);
+        ActT u1 = F.alloc((size_t)B * cH * cW, b.c1.cout, false, true);
+        ActT u2 = F.alloc((size_t)B * oH * oW, b.c2.cout, false, true);
         GIMB_CHECK(ctx.dry || !A.overflow, "backbone: workspace exhausted");
-        GIMB_TRY(run_conv(ctx, b.c1, cur, B, cH, cW, 1, ACT_RELU, nullptr, u1));
-        GIMB_TRY(run_conv(ctx, b.c2, u1, B, cH, cW, b.stride, ACT_RELU, nullptr, u2));
-        if (b.has_ds) GIMB_TRY(run_conv(ctx, b.ds, cur, B, cH, cW, b.stride, ACT_NONE, nullptr, xo));
-        // identity (xo) is read and overwritten element-wise by the same thread: in-place is safe
-        GIMB_TRY(run_conv(ctx, b.c3, u2, B, oH, oW, 1, ACT_RELU, xo, xo));
+        GIMB_TRY(run_conv(F, b.c1, cur, B, cH, cW, 1, ACT_RELU, nullptr, u1));
+        GIMB_TRY(run_conv(F, b.c2, u1, B, cH, cW, b.stride, ACT_RELU, nullptr, u2));
+        if (b.has_ds) {
+          ActT idn;  // the projected identity is only ever read as fp32 residual
+          idn.f32 = xo.f32; idn.C = xo.C;
+          GIMB_TRY(run_conv(F, b.ds, cur, B, cH, cW, b.stride, ACT_NONE, nullptr, idn));
+        }
+        // identity (xo.f32) is read and overwritten element-wise by the same thread: in-place is safe
+        GIMB_TRY(run_conv(F, b.c3, u2, B, oH, oW, 1, ACT_RELU, xo.f32, xo));
         A.release(mk2);
         cur = xo; cH = oH; cW = oW;
       }
@@ -175,79 +294,90 @@ int backbone(Ctx& ctx, gimb_loftr* m, const float* color, int B, int H, int W, f
     A.release(mk);
   }
   // FPN
-  GIMB_TRY(run_conv(ctx, m->l3out, x3, B, H8, W8, 1, ACT_NONE, nullptr, feat_c));
-  float* x2s = A.alloc<float>(P4 * 256);
-  float* x2t = A.alloc<float>(P4 * 256);
-  float* x2o = A.alloc<float>(P4 * 196);
-  float* x1s = A.alloc<float>(P2 * 196);
-  float* x1t = A.alloc<float>(P2 * 196);
+  ActT fc; fc.f32 = feat_c; fc.C = 256;
+  ActT ffm; ffm.f32 = feat_f; ffm.C = 128;
+  GIMB_TRY(run_conv(F, m->l3out, xs[2], B, H8, W8, 1, ACT_NONE, nullptr, fc));
+  ActT x2s = F.alloc(P4, 256, true, true);   // 1x1(x2) fp32, then (+ upsampled x3_out) as planes
+  ActT x2t = F.alloc(P4, 256, false, true);
+  ActT x2o = F.alloc(P4, 196, true, false);
+  ActT x1s = F.alloc(P2, 196, true, true);
+  ActT x1t = F.alloc(P2, 196, false, true);
   GIMB_CHECK(ctx.dry || !A.overflow, "backbone: workspace exhausted");
-  GIMB_TRY(run_conv(ctx, m->l2out, x2, B, H4, W4, 1, ACT_NONE, nullptr, x2s));
-  GIMB_TRY(upsample2x_add(ctx, feat_c, B, H8, W8, 256, x2s));
-  GIMB_TRY(run_conv(ctx, m->l2c1, x2s, B, H4, W4, 1, ACT_LEAKY, nullptr, x2t));
-  GIMB_TRY(run_conv(ctx, m->l2c2, x2t, B, H4, W4, 1, ACT_NONE, nullptr, x2o));
-  GIMB_TRY(run_conv(ctx, m->l1out, x1, B, H2, W2, 1, ACT_NONE, nullptr, x1s));
-  GIMB_TRY(upsample2x_add(ctx, x2o, B, H4, W4, 196, x1s));
-  GIMB_TRY(run_conv(ctx, m->l1c1, x1s, B, H2, W2, 1, ACT_LEAKY, nullptr, x1t));
-  GIMB_TRY(run_conv(ctx, m->l1c2, x1t, B, H2, W2, 1, ACT_NONE, nullptr, feat_f));
+  {
+    ActT o; o.f32 = x2s.f32; o.C = 256;
+    GIMB_TRY(run_conv(F, m->l2out, xs[1], B, H4, W4, 1, ACT_NONE, nullptr, o));
+  }
+  GIMB_TRY(upsample2x_add(ctx, feat_c, B, H8, W8, 256, x2s.f32, x2s.planes()));
+  GIMB_TRY(run_conv(F, m->l2c1, x2s, B, H4, W4, 1, ACT_LEAKY, nullptr, x2t));
+  GIMB_TRY(run_conv(F, m->l2c2, x2t, B, H4, W4, 1, ACT_NONE, nullptr, x2o));
+  {
+    ActT o; o.f32 = x1s.f32; o.C = 196;
+    GIMB_TRY(run_conv(F, m->l1out, xs[0], B, H2, W2, 1, ACT_NONE, nullptr, o));
+  }
+  GIMB_TRY(upsample2x_add(ctx, x2o.f32, B, H4, W4, 196, x1s.f32, x1s.planes()));
+  GIMB_TRY(run_conv(F, m->l1c1, x1s, B, H2, W2, 1, ACT_LEAKY, nullptr, x1t));
+  GIMB_TRY(run_conv(F, m->l1c2, x1t, B, H2, W2, 1, ACT_NONE, nullptr, ffm));
   A.release(mark);
   return 0;
 }
 
-int linear(Ctx& ctx, const float* x, const float* x2, int64_t rows, int C1, int C2, const float* w, int cout, int act0,
-           int act1, int split, float div, const uint8_t* row_mask, float* out) {
-  ConvGemm g;
-  g.in = x; g.in2 = x2; g.B = 1; g.H = (int)rows; g.W = 1; g.C1 = C1; g.C2 = C2;
-  g.OH = (int)rows; g.OW = 1;
-  g.w = w; g.Cout = cout; g.act0 = act0; g.act1 = act1; g.act_split = split; g.div = div; g.row_mask = row_mask;
-  g.out = out;
-  return conv_gemm(ctx, g);
+int linear(Fwd& F, const Wt& wt, const ActT& x, const ActT* x2, int64_t rows, int C1, int C2, int cout, int act0, int act1,
+           int split, float div, const uint8_t* row_mask, const ActT& out) {
+  Epi e;
+  e.act0 = act0; e.act1 = act1; e.act_split = split; e.div = div; e.row_mask = row_mask;
+  return gemm(F, wt, C1, C2, cout, 1, 1, x, x2, 1, (int)rows, 1, e, out);
 }
 
 // LoFTREncoderLayer.forward (networks/loftr/submodules/transformer.py:35-58); x is updated in place.
 // n sequences; x [n, L, C], src [n, S, C].  fine == true selects the per-match attention kernel.
-int encoder_layer(Ctx& ctx, const EncLayer& e, float* x, const float* src, int64_t n, int L, int S, int C, int nhead,
+int encoder_layer(Fwd& F, const EncLayer& e, const ActT& x, const ActT& src, int64_t n, int L, int S, int C, int nhead,
                   const uint8_t* xmask, const uint8_t* smask, bool fine) {
+  Ctx& ctx = F.ctx;
   Arena& A = ctx.arena;
   size_t mark = A.mark();
   const int64_t RL = n * L, RS = n * S;
-  float* q = A.alloc<float>((size_t)RL * C);
-  float* kv = A.alloc<float>((size_t)RS * 2 * C);
-  float* msg = A.alloc<float>((size_t)RL * C);
-  float* mrg = A.alloc<float>((size_t)RL * C);
-  float* hid = A.alloc<float>((size_t)RL * 2 * C);
+  ActT q = F.alloc(RL, C, true, false);
+  ActT kv = F.alloc(RS, 2 * C, true, false);
+  ActT msg = F.alloc(RL, C, false, true);       // attention output -> merge GEMM operand
+  ActT mrg = F.alloc(RL, C, true, true);        // merge output (fp32), LayerNorm'd into planes
+  ActT hid = F.alloc(RL, 2 * C, false, true);
+  ActT o2 = F.alloc(RL, C, true, false);
   GIMB_CHECK(ctx.dry || !A.overflow, "encoder_layer: workspace exhausted");
-  GIMB_TRY(linear(ctx, x, nullptr, RL, C, 0, e.q, C, ACT_ELU1, ACT_ELU1, 1 << 30, 1.f, xmask, q));
-  GIMB_TRY(linear(ctx, src, nullptr, RS, C, 0, e.kv, 2 * C, ACT_ELU1, ACT_DIVS, C, (float)S, smask, kv));
+  GIMB_TRY(linear(F, e.q, x, nullptr, RL, C, 0, C, ACT_ELU1, ACT_ELU1, 1 << 30, 1.f, xmask, q));
+  GIMB_TRY(linear(F, e.kv, src, nullptr, RS, C, 0, 2 * C, ACT_ELU1, ACT_DIVS, C, (float)S, smask, kv));
   if (fine)
-    GIMB_TRY(fine_attention(ctx, q, kv, n, L, C, nhead, msg));
+    GIMB_TRY(fine_attention(ctx, q.f32, kv.f32, n, L, C, nhead, msg.f32, msg.planes()));
   else
-    GIMB_TRY(linear_attention(ctx, q, kv, (int)n, L, S, C, nhead, msg));
-  GIMB_TRY(linear(ctx, msg, nullptr, RL, C, 0, e.merge, C, ACT_NONE, ACT_NONE, 1 << 30, 1.f, nullptr, mrg));
-  GIMB_TRY(layernorm(ctx, mrg, e.n1g, e.n1b, nullptr, RL, C, mrg));
-  GIMB_TRY(linear(ctx, x, mrg, RL, C, C, e.mlp0, 2 * C, ACT_RELU, ACT_RELU, 1 << 30, 1.f, nullptr, hid));
-  GIMB_TRY(linear(ctx, hid, nullptr, RL, 2 * C, 0, e.mlp2, C, ACT_NONE, ACT_NONE, 1 << 30, 1.f, nullptr, msg));
-  GIMB_TRY(layernorm(ctx, msg, e.n2g, e.n2b, x, RL, C, x));
+    GIMB_TRY(linear_attention(ctx, q.f32, kv.f32, (int)n, L, S, C, nhead, msg.f32, msg.planes()));
+  {
+    ActT o; o.f32 = mrg.f32; o.C = C;
+    GIMB_TRY(linear(F, e.merge, msg, nullptr, RL, C, 0, C, ACT_NONE, ACT_NONE, 1 << 30, 1.f, nullptr, o));
+  }
+  GIMB_TRY(layernorm(ctx, mrg.f32, e.n1g, e.n1b, nullptr, RL, C, F.tc() ? nullptr : mrg.f32, mrg.planes()));
+  GIMB_TRY(linear(F, e.mlp0, x, &mrg, RL, C, C, 2 * C, ACT_RELU, ACT_RELU, 1 << 30, 1.f, nullptr, hid));
+  GIMB_TRY(linear(F, e.mlp2, hid, nullptr, RL, 2 * C, 0, C, ACT_NONE, ACT_NONE, 1 << 30, 1.f, nullptr, o2));
+  GIMB_TRY(layernorm(ctx, o2.f32, e.n2g, e.n2b, x.f32, RL, C, x.f32, x.planes()));
   A.release(mark);
   return 0;
 }
 
-// LocalFeatureTransformer.forward (transformer.py:80-101): (self, cross) x npairs.  t0 [n,L,C], t1 [n,S,C].
-// When the two token buffers are contiguous and equally shaped the self layers run as one batch of 2n.
-int feature_transformer(Ctx& ctx, const EncLayer* layers, int npairs, float* t0, float* t1, int64_t n, int L, int S,
-                        int C, int nhead, const uint8_t* m0, const uint8_t* m1, bool fine) {
-  const bool batched = (L == S) && (t1 == t0 + (size_t)n * L * C) && (m0 == nullptr || m1 == m0 + n * L);
+// LocalFeatureTransformer.forward (transformer.py:80-101): (self, cross) x npairs.  `tok` holds both token sets
+// back to back: rows [0, n*L) = feat0, rows [n*L, n*L + n*S) = feat1.  When L == S the self layers run as one batch.
+int feature_transformer(Fwd& F, const EncLayer* layers, int npairs, const ActT& tok, int64_t n, int L, int S, int C,
+                        int nhead, const uint8_t* m0, const uint8_t* m1, bool fine) {
+  const ActT t0 = tok, t1 = view_rows(tok, (size_t)n * L);
+  const bool batched = (L == S) && (m0 == nullptr || m1 == m0 + n * L);
   for (int i = 0; i < npairs; ++i) {
     const EncLayer& self = layers[2 * i];
     const EncLayer& cross = layers[2 * i + 1];
     if (batched) {
-      GIMB_TRY(encoder_layer(ctx, self, t0, t0, 2 * n, L, L, C, nhead, m0, m0, fine));
+      GIMB_TRY(encoder_layer(F, self, t0, t0, 2 * n, L, L, C, nhead, m0, m0, fine));
     } else {
-      GIMB_TRY(encoder_layer(ctx, self, t0, t0, n, L, L, C, nhead, m0, m0, fine));
-      GIMB_TRY(encoder_layer(ctx, self, t1, t1, n, S, S, C, nhead, m1, m1, fine));
+      GIMB_TRY(encoder_layer(F, self, t0, t0, n, L, L, C, nhead, m0, m0, fine));
+      GIMB_TRY(encoder_layer(F, self, t1, t1, n, S, S, C, nhead, m1, m1, fine));
     }
-    GIMB_TRY(encoder_layer(ctx, cross, t0, t1, n, L, S, C, nhead, m0, m1, fine));
-    GIMB_TRY(encoder_layer(ctx, cross, t1, t0, n, S, L, C, nhead, m1, m0, fine));
+    GIMB_TRY(encoder_layer(F, cross, t0, t1, n, L, S, C, nhead, m0, m1, fine));
+    GIMB_TRY(encoder_layer(F, cross, t1, t0, n, S, L, C, nhead, m1, m0, fine));
   }
   return 0;
 }
@@ -301,6 +431,7 @@ int copy_tap(Ctx& ctx, float* dst, const float* src, size_t nfloat) {
 // the whole forward; in dry mode only the arena is exercised (workspace planning).
 int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
   Arena& A = ctx.arena;
+  Fwd F{ctx, m};
   const int n = f.n;
   const int h0c = f.h0 / 8, w0c = f.w0 / 8, h1c = f.h1 / 8, w1c = f.w1 / 8;
   const int h0f = f.h0 / 2, w0f = f.w0 / 2, h1f = f.h1 / 2, w1f = f.w1 / 2;
@@ -312,11 +443,13 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
   Prof prof(m, ctx.stream, m->profiling && !ctx.dry);
   ctx.marker = &prof;
 
-  // persistent buffers (bottom of the stack)
-  float* fc0 = A.alloc<float>((size_t)n * L * C);   // FPN coarse maps, later the token buffers
-  float* fc1 = A.alloc<float>((size_t)n * S * C);
-  float* ff0 = A.alloc<float>((size_t)n * h0f * w0f * CF);
-  float* ff1 = A.alloc<float>((size_t)n * h1f * w1f * CF);
+  // persistent buffers (bottom of the stack): coarse tokens (both images back to back) and the fine maps
+  ActT tok = F.alloc((size_t)n * (L + S), C, true, true, true);
+  float* fc0 = tok.f32;
+  float* fc1 = tok.f32 + (size_t)n * L * C;
+  float* ff = A.alloc<float>((size_t)n * ((size_t)h0f * w0f + (size_t)h1f * w1f) * CF);
+  float* ff0 = ff;
+  float* ff1 = ff + (size_t)n * h0f * w0f * CF;
   uint8_t* maskbuf = nullptr;
   if (f.mask0) maskbuf = A.alloc<uint8_t>((size_t)n * (L + S));
   GIMB_CHECK(ctx.dry || !A.overflow, "forward: workspace too small");
@@ -336,14 +469,11 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
       }
       both = stage;
     }
-    // fc0/fc1 and ff0/ff1 are contiguous pairs (sizes are multiples of the arena alignment)
-    GIMB_CHECK(ctx.dry || (fc1 == fc0 + (size_t)n * L * C && ff1 == ff0 + (size_t)n * h0f * w0f * CF),
-               "internal: feature buffers not contiguous");
-    GIMB_TRY(backbone(ctx, m, both, 2 * n, f.h0, f.w0, fc0, ff0));
+    GIMB_TRY(backbone(F, both, 2 * n, f.h0, f.w0, fc0, ff0));
     A.release(mk);
   } else {
-    GIMB_TRY(backbone(ctx, m, f.color0, n, f.h0, f.w0, fc0, ff0));
-    GIMB_TRY(backbone(ctx, m, f.color1, n, f.h1, f.w1, fc1, ff1));
+    GIMB_TRY(backbone(F, f.color0, n, f.h0, f.w0, fc0, ff0));
+    GIMB_TRY(backbone(F, f.color1, n, f.h1, f.w1, fc1, ff1));
   }
   prof.mark("backbone");
   GIMB_TRY(copy_tap(ctx, taps.feat_c_backbone0, fc0, (size_t)n * L * C));
@@ -359,8 +489,11 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
                "position-encoding table for %dx%d / %dx%d not set (call gimb_loftr_set_pe)", h0c, w0c, h1c, w1c);
     pe0 = i0->second; pe1 = i1->second;
   }
-  GIMB_TRY(add_pe(ctx, fc0, pe0, n, L, C, fc0));
-  GIMB_TRY(add_pe(ctx, fc1, pe1, n, S, C, fc1));
+  {
+    const ActT t1 = view_rows(tok, (size_t)n * L);
+    GIMB_TRY(add_pe(ctx, fc0, pe0, n, L, C, fc0, tok.planes()));
+    GIMB_TRY(add_pe(ctx, fc1, pe1, n, S, C, fc1, t1.planes()));
+  }
   const uint8_t *cm0 = nullptr, *cm1 = nullptr;
   if (f.mask0) {
     cm0 = maskbuf; cm1 = maskbuf + (size_t)n * L;
@@ -369,7 +502,7 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
       GIMB_CUDA(cudaMemcpyAsync(maskbuf + (size_t)n * L, f.mask1, (size_t)n * S, cudaMemcpyDeviceToDevice, ctx.stream));
     }
   }
-  GIMB_TRY(feature_transformer(ctx, m->coarse, 4, fc0, fc1, n, L, S, C, 8, cm0, cm1, false));
+  GIMB_TRY(feature_transformer(F, m->coarse, 4, tok, n, L, S, C, 8, cm0, cm1, false));
   prof.mark("coarse_transformer");
   GIMB_TRY(copy_tap(ctx, taps.feat_c0, fc0, (size_t)n * L * C));
   GIMB_TRY(copy_tap(ctx, taps.feat_c1, fc1, (size_t)n * S * C));
@@ -407,16 +540,16 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
   for (int64_t m0 = 0; m0 < M; m0 += FINE_CHUNK) {
     const int64_t mc = std::min<int64_t>(FINE_CHUNK, M - m0);
     size_t mk = A.mark();
-    float* w0 = A.alloc<float>((size_t)mc * WW * CF);
-    float* w1 = A.alloc<float>((size_t)mc * WW * CF);
+    ActT win = F.alloc((size_t)2 * mc * WW, CF, true, true);  // windows of image0 then image1
+    const ActT w1v = view_rows(win, (size_t)mc * WW);
     GIMB_CHECK(ctx.dry || !A.overflow, "forward: workspace too small (fine stage)");
-    GIMB_TRY(fine_gather(ctx, ff0, h0f, w0f, CF, w0c, stride, Wn, o.b_ids, o.i_ids, m0, mc, w0));
-    GIMB_TRY(fine_gather(ctx, ff1, h1f, w1f, CF, w1c, stride, Wn, o.b_ids, o.j_ids, m0, mc, w1));
-    GIMB_TRY(feature_transformer(ctx, m->fine, 1, w0, w1, mc, WW, WW, CF, 8, nullptr, nullptr, true));
-    GIMB_TRY(copy_tap(ctx, taps.fine_win0 ? taps.fine_win0 + (size_t)m0 * WW * CF : nullptr, w0, (size_t)mc * WW * CF));
-    GIMB_TRY(copy_tap(ctx, taps.fine_win1 ? taps.fine_win1 + (size_t)m0 * WW * CF : nullptr, w1, (size_t)mc * WW * CF));
+    GIMB_TRY(fine_gather(ctx, ff0, h0f, w0f, CF, w0c, stride, Wn, o.b_ids, o.i_ids, m0, mc, win.f32, win.planes()));
+    GIMB_TRY(fine_gather(ctx, ff1, h1f, w1f, CF, w1c, stride, Wn, o.b_ids, o.j_ids, m0, mc, w1v.f32, w1v.planes()));
+    GIMB_TRY(feature_transformer(F, m->fine, 1, win, mc, WW, WW, CF, 8, nullptr, nullptr, true));
+    GIMB_TRY(copy_tap(ctx, taps.fine_win0 ? taps.fine_win0 + (size_t)m0 * WW * CF : nullptr, win.f32, (size_t)mc * WW * CF));
+    GIMB_TRY(copy_tap(ctx, taps.fine_win1 ? taps.fine_win1 + (size_t)m0 * WW * CF : nullptr, w1v.f32, (size_t)mc * WW * CF));
     FineMatchArgs fm;
-    fm.f0 = w0; fm.f1 = w1; fm.m0 = m0; fm.m = mc; fm.WW = WW; fm.C = CF; fm.Wn = Wn;
+    fm.f0 = win.f32; fm.f1 = w1v.f32; fm.m0 = m0; fm.m = mc; fm.WW = WW; fm.C = CF; fm.Wn = Wn;
     fm.fscale = (float)f.h0 / (float)h0f;
     fm.sim_scale = (float)(1.0 / sqrt((double)CF));
     fm.b_ids = o.b_ids; fm.scale1 = f.scale0 ? f.scale1 : nullptr;
@@ -486,9 +619,29 @@ int gimb_loftr_create(const void* blob, size_t nbytes, const gimb_loftr_cfg* cfg
     std::string name(ent[i].name, strnlen(ent[i].name, sizeof(ent[i].name)));
     m->tensors[name] = {(const float*)(m->dblob + ent[i].offset), sh};
   }
-  if (build_model(m) != 0) {
-    gimb_loftr_destroy(m);
-    return 1;
+  {
+    // pass 1 sizes the fp16 weight planes, pass 2 fills them (tcgen05 engine operands)
+    Ctx cctx;
+    cctx.sm_count = m->sm_count;
+    m->dplanes_top = 0;
+    if (build_model(m, cctx) != 0) {
+      gimb_loftr_destroy(m);
+      return 1;
+    }
+    m->dplanes_bytes = m->dplanes_top + 256;
+    if (cudaMalloc(&m->dplanes, m->dplanes_bytes) != cudaSuccess) {
+      gimb_loftr_destroy(m);
+      set_error("cudaMalloc of %zu weight-plane bytes failed", m->dplanes_bytes);
+      return 1;
+    }
+    cudaMemset(m->dplanes, 0, m->dplanes_bytes);
+    m->dplanes_top = 0;
+    if (build_model(m, cctx) != 0 || cudaDeviceSynchronize() != cudaSuccess) {
+      gimb_loftr_destroy(m);
+      return 1;
+    }
+    const char* eng = getenv("GIMB_ENGINE");
+    if (eng && eng[0] == 's') m->engine = ENGINE_SIMT;
   }
   if (cudaMallocHost(&m->host_count, sizeof(int64_t)) != cudaSuccess) {
     gimb_loftr_destroy(m);
@@ -503,6 +656,7 @@ void gimb_loftr_destroy(gimb_loftr* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->dblob) cudaFree(h->dblob);
+  if (h->dplanes) cudaFree(h->dplanes);
   for (auto& kv : h->pe_cache) cudaFree(kv.second);
   if (h->host_count) cudaFreeHost(h->host_count);
   delete h;
@@ -636,6 +790,12 @@ int gimb_loftr_forward_host(gimb_loftr* h, const float* color0, const float* col
 }
 
 uint64_t gimb_loftr_launch_count(gimb_loftr* h) { return h ? h->launches : 0; }
+
+int gimb_loftr_set_engine(gimb_loftr* h, int engine) {
+  GIMB_CHECK(h && (engine == ENGINE_SIMT || engine == ENGINE_TC), "gimb_loftr_set_engine: bad argument");
+  h->engine = engine;
+  return 0;
+}
 
 int gimb_loftr_set_profiling(gimb_loftr* h, int enabled) {
   GIMB_CHECK(h, "null handle");

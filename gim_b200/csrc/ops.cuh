@@ -1,6 +1,7 @@
 // ops.cuh - host-side launchers of every kernel in libgimb200 (declarations).
 #pragma once
 #include "common.cuh"
+#include "umma_gemm.cuh"
 
 namespace gimb {
 
@@ -31,25 +32,29 @@ int conv_gemm(Ctx& ctx, const ConvGemm& p);
 // stem: 7x7 stride-2 pad-3 conv 3->64 + folded BN + ReLU; NCHW fp32 in, NHWC out
 // (networks/loftr/backbone/resnet.py:158,230).
 int stem_conv7x7(Ctx& ctx, const float* in_nchw, int B, int H, int W, const float* w /*[64][7][7][3]*/,
-                 const float* scale, const float* bias, float* out_nhwc);
+                 const float* scale, const float* bias, float* out_nhwc, const SplitPlanes* planes = nullptr);
 
 // out[b, y, x, c] += bilinear_2x(align_corners=True)(low)[b, y, x, c]   (resnet.py:321-327)
-int upsample2x_add(Ctx& ctx, const float* low, int B, int h, int w, int C, float* out /*[B,2h,2w,C]*/);
+// with `planes` the sum is written as split fp16 planes (pad channels zeroed) instead of back into `out`
+int upsample2x_add(Ctx& ctx, const float* low, int B, int h, int w, int C, float* out /*[B,2h,2w,C]*/,
+                   const SplitPlanes* planes = nullptr);
 
 // tokens[b, l, c] = feat[b, l, c] + pe[l, c]   (loftr.py:74-75, position_encoding.py:43)
-int add_pe(Ctx& ctx, const float* feat, const float* pe, int B, int L, int C, float* tokens);
+int add_pe(Ctx& ctx, const float* feat, const float* pe, int B, int L, int C, float* tokens,
+           const SplitPlanes* planes = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over the last dim (eps 1e-5) with optional residual: out = (res ? res : 0) + LN(x)
+// `out` (fp32) and `planes` (split fp16, optionally with the h8 plane) are both optional sinks.
 int layernorm(Ctx& ctx, const float* x, const float* gamma, const float* beta, const float* res,
-              int64_t rows, int C, float* out);
+              int64_t rows, int C, float* out, const SplitPlanes* planes = nullptr);
 
 // Linear attention (networks/loftr/submodules/attentions.py:31-47), coarse flavour: D = 32 per head.
 //   kv [B, S, 2C]: columns [0,C) = K' = elu(k)+1 (masked), [C,2C) = V/S (masked)
 //   q  [B, L, C]  = Q' = elu(q)+1 (masked)
 //   msg[b, l, h*D+v] = (sum_d Q'[l,h,d] KV[h,d,v]) / (sum_d Q'[l,h,d] Ksum[h,d] + 1e-6) * S
 int linear_attention(Ctx& ctx, const float* q, const float* kv, int B, int L, int S, int C, int nhead,
-                     float* msg);
+                     float* msg, const SplitPlanes* planes = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // coarse matching (networks/loftr/utils/coarse_matching.py:88-259)
@@ -78,9 +83,10 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& a);
 // gather W x W windows around stride*cell centres: out [M, WW, C]
 int fine_gather(Ctx& ctx, const float* feat_f /*[N,hf,wf,C]*/, int hf, int wf, int C, int wc /*coarse width*/,
                 int stride, int Wn, const int64_t* b_ids, const int64_t* ids, int64_t m0, int64_t m,
-                float* out);
+                float* out, const SplitPlanes* planes = nullptr);
 // per-match linear attention with D = 16 per head, sequence WW (<= 32)
-int fine_attention(Ctx& ctx, const float* q, const float* kv, int64_t M, int WW, int C, int nhead, float* msg);
+int fine_attention(Ctx& ctx, const float* q, const float* kv, int64_t M, int WW, int C, int nhead, float* msg,
+                   const SplitPlanes* planes = nullptr);
 struct FineMatchArgs {
   const float* f0;  // [m, WW, C]
   const float* f1;

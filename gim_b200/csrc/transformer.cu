@@ -4,6 +4,7 @@
 #include <algorithm>
 
 #include "ops.cuh"
+#include "split.cuh"
 
 namespace gimb {
 namespace {
@@ -19,7 +20,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int VPT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, const float* __restrict__ res,
-                                                        int64_t rows, float* __restrict__ out) {
+                                                        int64_t rows, float* __restrict__ out, const PlanesDev sp) {
   constexpr int C = 32 * VPT;
   const int lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.y = r.y + fmaf((v[i * 4 + 1] - mean) * rstd, g.y, b.y);
     o.z = r.z + fmaf((v[i * 4 + 2] - mean) * rstd, g.z, b.z);
     o.w = r.w + fmaf((v[i * 4 + 3] - mean) * rstd, g.w, b.w);
-    *reinterpret_cast<float4*>(out + row * C + c) = o;
+    if (out) *reinterpret_cast<float4*>(out + row * C + c) = o;
+    if (sp.hi) split4_store(sp, (size_t)row * sp.ld + c, o.x, o.y, o.z, o.w);
   }
 }
 
@@ -128,7 +130,7 @@ __global__ void kv_reduce_kernel(const float* __restrict__ part, int nsplit, flo
 // one CTA = 8 warps, each warp walks rows; KV of all heads of image b lives in shared memory.
 __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ q, const float* __restrict__ kvf,
                                                          int L, int C, int nhead, float vlen, int rows_per_cta,
-                                                         float* __restrict__ msg) {
+                                                         float* __restrict__ msg, const PlanesDev sp) {
   extern __shared__ float sm[];  // [nhead][KV_STRIDE]
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
   const int l1 = min(L, l0 + rows_per_cta);
   for (int l = l0 + warp; l < l1; l += 8) {
     const float* qr = q + ((size_t)b * L + l) * C;
-    float* mr = msg + ((size_t)b * L + l) * C;
+    const size_t grow = (size_t)b * L + l;
     for (int h = 0; h < nhead; ++h) {
       const float* kvh = sm + h * KV_STRIDE;
       float qv = qr[h * 32 + lane];
@@ -147,7 +149,13 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
 #pragma unroll
       for (int d = 0; d < 32; ++d) o = fmaf(__shfl_sync(0xffffffffu, qv, d), kvh[d * 32 + lane], o);
       float z = 1.f / (zden + 1e-6f);
-      mr[h * 32 + lane] = o * z * vlen;
+      const float r = o * z * vlen;
+      if (msg) msg[grow * C + h * 32 + lane] = r;
+      if (sp.hi) {
+        const __half hh = __float2half_rn(r);
+        sp.hi[grow * sp.ld + h * 32 + lane] = hh;
+        sp.lo[grow * sp.ld + h * 32 + lane] = __float2half_rn((r - __half2float(hh)) * kSplitScale);
+      }
     }
   }
 }
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
 // threads per match; thread c owns channel c: (head h = c / 16, value index v = c % 16).
 template <int C, int D, int MAXWW>
 __global__ void __launch_bounds__(C) fine_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv,
-                                                      int64_t M, int WW, float* __restrict__ msg) {
+                                                      int64_t M, int WW, float* __restrict__ msg, const PlanesDev sp) {
   __shared__ float Qs[MAXWW][C];
   __shared__ float Ks[MAXWW][C];
   const int c = threadIdx.x;
@@ -200,7 +208,13 @@ __global__ void __launch_bounds__(C) fine_attn_kernel(const float* __restrict__ 
         o = fmaf(qq, kvacc[d], o);
         zden = fmaf(qq, ksum[d], zden);
       }
-      msg[(m * WW + l) * C + c] = o * (1.f / (zden + 1e-6f)) * (float)WW;
+      const float r = o * (1.f / (zden + 1e-6f)) * (float)WW;
+      if (msg) msg[(m * WW + l) * C + c] = r;
+      if (sp.hi) {
+        const __half hh = __float2half_rn(r);
+        sp.hi[(m * WW + l) * sp.ld + c] = hh;
+        sp.lo[(m * WW + l) * sp.ld + c] = __float2half_rn((r - __half2float(hh)) * kSplitScale);
+      }
     }
     __syncthreads();
   }
@@ -209,20 +223,23 @@ __global__ void __launch_bounds__(C) fine_attn_kernel(const float* __restrict__ 
 }  // namespace
 
 int layernorm(Ctx& ctx, const float* x, const float* gamma, const float* beta, const float* res, int64_t rows,
-              int C, float* out) {
+              int C, float* out, const SplitPlanes* planes) {
+  const PlanesDev sp = planes ? dev(*planes) : PlanesDev{nullptr, nullptr, nullptr, 0};
   GIMB_CHECK(C == 256 || C == 128, "layernorm: C must be 128 or 256 (got %d)", C);
   if (ctx.dry || rows == 0) return 0;
   int blocks = (int)cdiv64(rows, 8);
   if (C == 256)
-    layernorm_kernel<8><<<blocks, 256, 0, ctx.stream>>>(x, gamma, beta, res, rows, out);
+    layernorm_kernel<8><<<blocks, 256, 0, ctx.stream>>>(x, gamma, beta, res, rows, out, sp);
   else
-    layernorm_kernel<4><<<blocks, 256, 0, ctx.stream>>>(x, gamma, beta, res, rows, out);
+    layernorm_kernel<4><<<blocks, 256, 0, ctx.stream>>>(x, gamma, beta, res, rows, out, sp);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;
 }
 
-int linear_attention(Ctx& ctx, const float* q, const float* kv, int B, int L, int S, int C, int nhead, float* msg) {
+int linear_attention(Ctx& ctx, const float* q, const float* kv, int B, int L, int S, int C, int nhead, float* msg,
+                     const SplitPlanes* planes) {
+  const PlanesDev sp = planes ? dev(*planes) : PlanesDev{nullptr, nullptr, nullptr, 0};
   GIMB_CHECK(C == nhead * 32, "linear_attention: coarse flavour needs head dim 32");
   const int BH = B * nhead;
   int nsplit = std::max(1, std::min(cdiv(ctx.sm_count * 4, BH), cdiv(S, 4 * KV_CHUNK)));
@@ -239,7 +256,7 @@ int linear_attention(Ctx& ctx, const float* q, const float* kv, int B, int L, in
     const int rows_per_cta = 64;
     size_t smem = (size_t)nhead * KV_STRIDE * sizeof(float);
     attn_apply_kernel<<<dim3(cdiv(L, rows_per_cta), B), 256, smem, ctx.stream>>>(q, kvf, L, C, nhead, (float)S,
-                                                                                   rows_per_cta, msg);
+                                                                                   rows_per_cta, msg, sp);
     GIMB_LAUNCH_CHECK();
     ctx.launches += 3;
   }
@@ -247,11 +264,13 @@ int linear_attention(Ctx& ctx, const float* q, const float* kv, int B, int L, in
   return 0;
 }
 
-int fine_attention(Ctx& ctx, const float* q, const float* kv, int64_t M, int WW, int C, int nhead, float* msg) {
+int fine_attention(Ctx& ctx, const float* q, const float* kv, int64_t M, int WW, int C, int nhead, float* msg,
+                   const SplitPlanes* planes) {
+  const PlanesDev sp = planes ? dev(*planes) : PlanesDev{nullptr, nullptr, nullptr, 0};
   GIMB_CHECK(C == 128 && nhead == 8 && WW <= 25, "fine_attention: built for C=128, 8 heads, WW<=25");
   if (ctx.dry || M == 0) return 0;
   int blocks = (int)std::min<int64_t>(M, (int64_t)ctx.sm_count * 32);
-  fine_attn_kernel<128, 16, 25><<<blocks, 128, 0, ctx.stream>>>(q, kv, M, WW, msg);
+  fine_attn_kernel<128, 16, 25><<<blocks, 128, 0, ctx.stream>>>(q, kv, M, WW, msg, sp);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;

@@ -6,8 +6,12 @@
 //   warp 1      MMA issuer    : one elected lane issues 3 x tcgen05.mma.kind::f16 (M=128, N<=256, K=16) per k16 step
 //                               [A_hi*B_h8 + A_hi*B_lo + A_lo*B_hi] into a double-buffered fp32 TMEM accumulator,
 //                               tcgen05.commit frees smem stages / publishes the accumulator
-//   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns), 2^-8 rescale, folded-BN scale/bias, residual,
-//                               activation, row mask, fp32 store and/or re-split into fp16 planes for the next layer
+//   warps 4..11 epilogue      : the tensor core accumulates only CHUNK_KB k-blocks at a time; the chunks are summed
+//                               in fp32 registers with round-to-nearest (tcgen05.ld, 32 lanes x 32 columns).  The MMA
+//                               accumulator truncates, and a long in-TMEM accumulation biases the result by ~K/16 ulp
+//                               (measured: 5x the fp32 FMA error at K = 1764); short chunks + RN adds keep the result
+//                               in the fp32 class.  Then 2^-8 rescale, folded-BN scale/bias, residual, activation,
+//                               row mask, fp32 store and/or re-split into fp16 planes for the next layer
 //
 // Tile: BM = 128 output rows (mode 0: consecutive rows; mode 1: an 8 x 16 pixel patch of one image),
 //       BN = whole N up to 256 (rounded to 16), BK = 32 fp16 (64-byte rows).
@@ -24,8 +28,10 @@ constexpr int BK = 32;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 8 KB
 constexpr int TH = 8, TW = 16;
 constexpr int MAX_STAGES = 8;
-constexpr int NUM_EPI_WARPS = 4;
-constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int NUM_EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each owning alternate 32-column groups
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;  // warpgroup 0: TMA, MMA, 2 idle warps; warpgroups 1-2: epilogue
+constexpr int REGS_LOW = 40, REGS_HIGH = 232;           // setmaxnreg split: 4*32*40 + 8*32*232 = 64512 <= 65536
+constexpr int CHUNK_KB = 2;        // k-blocks (of 32) accumulated inside the tensor core before the fp32 (RN) drain
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
@@ -45,7 +51,7 @@ struct KParams {
   int ldk;
   int N, n_tiles, bn;
   int stages, stage_bytes;
-  int num_tiles, num_kb;
+  int num_tiles, num_kb, num_chunks;
   unsigned idesc;
   const float* scale;
   const float* bias;
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(tfull_bar(b), 1);
-        mbar_init(tempty_bar(b), NUM_EPI_WARPS * 32);
+        mbar_init(tempty_bar(b), NUM_EPI_WARPS);
       }
       fence_barrier_init();
     }
@@ -216,6 +222,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 
   if (warp == 0) {
     // =============================================================== TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LOW));
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -264,47 +271,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LOW));
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int local = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++local) {
-        const int buf = local & 1;
-        const uint32_t aphase = (local >> 1) & 1;
-        mbar_wait(tempty_bar(buf), aphase ^ 1);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * ACC_COLS;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+      uint32_t cc = 0;  // chunk counter across tiles: TMEM buffer = cc & 1
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        int kb = 0;
+        for (int ch = 0; ch < p.num_chunks; ++ch, ++cc) {
+          const int buf = cc & 1;
+          mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t sA = base + stage * p.stage_bytes;
-          const uint32_t sB = sA + 2 * A_TILE_BYTES;
+          const uint32_t tacc = tmem_base + buf * ACC_COLS;
+          const int kb_end = min(p.num_kb, kb + CHUNK_KB);
+          bool first = true;
+          for (; kb < kb_end; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sA = base + stage * p.stage_bytes;
+            const uint32_t sB = sA + 2 * A_TILE_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint32_t koff = kk * 32;  // 16 fp16 = 32 bytes inside the 64-byte swizzle row
-            const uint64_t a_hi = make_desc_sw64(sA + koff);
-            const uint64_t a_lo = make_desc_sw64(sA + A_TILE_BYTES + koff);
-            const uint64_t b_h8 = make_desc_sw64(sB + koff);
-            const uint64_t b_lo = make_desc_sw64(sB + b_plane + koff);
-            const uint64_t b_hi = make_desc_sw64(sB + 2 * b_plane + koff);
-            umma_f16(tacc, a_hi, b_h8, p.idesc, (kb | kk) != 0);
-            umma_f16(tacc, a_hi, b_lo, p.idesc, 1);
-            umma_f16(tacc, a_lo, b_hi, p.idesc, 1);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint32_t koff = kk * 32;  // 16 fp16 = 32 bytes inside the 64-byte swizzle row
+              const uint64_t a_hi = make_desc_sw64(sA + koff);
+              const uint64_t a_lo = make_desc_sw64(sA + A_TILE_BYTES + koff);
+              const uint64_t b_h8 = make_desc_sw64(sB + koff);
+              const uint64_t b_lo = make_desc_sw64(sB + b_plane + koff);
+              const uint64_t b_hi = make_desc_sw64(sB + 2 * b_plane + koff);
+              umma_f16(tacc, a_hi, b_h8, p.idesc, first ? 0u : 1u);
+              umma_f16(tacc, a_hi, b_lo, p.idesc, 1);
+              umma_f16(tacc, a_lo, b_hi, p.idesc, 1);
+              first = false;
+            }
+            umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          umma_commit(tfull_bar(buf));      // chunk accumulator complete
         }
-        umma_commit(tfull_bar(buf));      // accumulator complete
       }
     }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LOW));
   } else {
     // =============================================================== epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_HIGH));
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;     // which alternate 32-column groups this warp owns
     const int r_in_tile = q * 32 + lane;  // accumulator row owned by this thread
-    int local = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++local) {
-      const int buf = local & 1;
-      const uint32_t aphase = (local >> 1) & 1;
+    uint32_t cc = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
       const int n0 = tc.n_tile * p.bn;
       long long row;
@@ -319,17 +334,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       }
       float rmask = 1.f;
       if (p.row_mask && row_ok) rmask = (float)p.row_mask[row];
-      mbar_wait(tfull_bar(buf), aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
-        uint32_t raw32[32];
-        tmem_ld32(taddr + c0, raw32);
-        tmem_ld_wait();
-        if (!row_ok) continue;
+
+      // ---- drain the chunk accumulators into fp32 registers (round-to-nearest adds)
+      float acc[4][32];
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[gi][j] = 0.f;
+      for (int ch = 0; ch < p.num_chunks; ++ch, ++cc) {
+        const int buf = cc & 1;
+        mbar_wait(tfull_bar(buf), (cc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          const int c0 = (gi * 2 + half) * 32;
+          if (c0 < p.bn) {
+            uint32_t raw32[32];
+            tmem_ld32(taddr + c0, raw32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[gi][j] += __uint_as_float(raw32[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
+      }
+
+      // ---- final epilogue from registers
+      if (!row_ok) continue;
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        const int c0 = (gi * 2 + half) * 32;
+        if (c0 >= p.bn) continue;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw32[j]) * (1.f / kSplitScale);
+        for (int j = 0; j < 32; ++j) v[j] = acc[gi][j] * (1.f / kSplitScale);
         const int cbase = n0 + c0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -380,8 +421,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(buf));
     }
   }
 
@@ -541,6 +580,7 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
   p.stages = std::max(1, std::min(p.stages, std::max(2, p.num_kb)));
   p.num_tiles = m_tiles * p.n_tiles;
+  p.num_chunks = cdiv(p.num_kb, CHUNK_KB);
   p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
   p.scale = g.scale; p.bias = g.bias; p.residual = g.residual; p.row_mask = g.row_mask;
   p.act0 = g.act0; p.act1 = g.act1; p.act_split = g.act_split; p.div = g.div;
