@@ -396,7 +396,9 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
   GIMB_CHECK(c.C % 16 == 0, "coarse_match: C must be a multiple of 16");
   GIMB_CHECK((c.mask0 == nullptr) == (c.mask1 == nullptr), "coarse_match: mask0/mask1 go together");
   GIMB_CHECK((c.scale0 == nullptr) == (c.scale1 == nullptr), "coarse_match: scale0/scale1 go together");
-  const int tiles_m = cdiv(c.L, BM), tiles_n = cdiv(c.S, BN);
+  const bool tc = c.planes0 != nullptr && c.planes1 != nullptr && c.conf_matrix == nullptr;
+  int tiles_m = cdiv(c.L, BM), tiles_n = cdiv(c.S, BN);  // partials per column / per row
+  if (tc) umma_corr_parts(c.L, c.S, &tiles_n, &tiles_m);
   const size_t NL = (size_t)c.N * c.L, NS = (size_t)c.N * c.S;
   size_t mark = ctx.arena.mark();
   float2* rowpart = ctx.arena.alloc<float2>(NL * tiles_n);
@@ -424,9 +426,18 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
     a.tiles_m = tiles_m; a.tiles_n = tiles_n;
     a.rowpart = rowpart; a.colpart = colpart; a.rowstat = rowstat; a.colstat = colstat;
     a.rowbest = rowbest; a.colbest = colbest; a.conf_matrix = c.conf_matrix;
-    dim3 grid(tiles_m, tiles_n, c.N);
-    corr_stats_kernel<<<grid, NTHREADS, smem_bytes<BN>(), ctx.stream>>>(a);
-    GIMB_LAUNCH_CHECK();
+    dim3 grid(cdiv(c.L, BM), cdiv(c.S, BN), c.N);
+    UmmaCorr uc;
+    if (tc) {
+      uc.f0 = *c.planes0; uc.f1 = *c.planes1; uc.N = c.N; uc.L = c.L; uc.S = c.S; uc.C = c.C;
+      uc.mask0 = c.mask0; uc.mask1 = c.mask1; uc.temperature = c.temperature; uc.thr = c.thr;
+      uc.rowpart = rowpart; uc.colpart = colpart; uc.rowstat = rowstat; uc.colstat = colstat;
+      uc.rowbest = rowbest; uc.colbest = colbest;
+      GIMB_TRY(umma_corr(ctx, uc, 0));
+    } else {
+      corr_stats_kernel<<<grid, NTHREADS, smem_bytes<BN>(), ctx.stream>>>(a);
+      GIMB_LAUNCH_CHECK();
+    }
     ctx.mark("corr_stats");
     merge_stats_kernel<<<(unsigned)cdiv64(NL, 256), 256, 0, ctx.stream>>>(rowpart, tiles_n, rowstat, NL);
     GIMB_LAUNCH_CHECK();
@@ -435,8 +446,12 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
     GIMB_CUDA(cudaMemsetAsync(rowbest, 0, NL * sizeof(unsigned long long), ctx.stream));
     GIMB_CUDA(cudaMemsetAsync(colbest, 0, NS * sizeof(unsigned int), ctx.stream));
     ctx.mark("corr_merge");
-    corr_conf_kernel<<<grid, NTHREADS, smem_bytes<BN>(), ctx.stream>>>(a);
-    GIMB_LAUNCH_CHECK();
+    if (tc) {
+      GIMB_TRY(umma_corr(ctx, uc, 1));
+    } else {
+      corr_conf_kernel<<<grid, NTHREADS, smem_bytes<BN>(), ctx.stream>>>(a);
+      GIMB_LAUNCH_CHECK();
+    }
     ctx.mark("corr_conf");
     ctx.launches += 4;
 

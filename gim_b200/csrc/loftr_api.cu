@@ -518,6 +518,8 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
   cm.b_ids = o.b_ids; cm.i_ids = o.i_ids; cm.j_ids = o.j_ids;
   cm.mconf = o.mconf; cm.mkpts0_c = o.mkpts0_c; cm.mkpts1_c = o.mkpts1_c;
   cm.count = dcount; cm.conf_matrix = taps.conf_matrix;
+  const ActT tok1 = view_rows(tok, (size_t)n * L);
+  if (F.tc()) { cm.planes0 = tok.planes(); cm.planes1 = tok1.planes(); }
   GIMB_TRY(coarse_match(ctx, cm));
   prof.mark("select_compact");
 

@@ -64,7 +64,21 @@ struct KParams {
   __half* out_lo;
   __half* out_h8;
   int ldp;
+  // ---- coarse-matching sweeps (EPI_CORR_*): batch of nb problems, A = f0[b] [L,C], B = f1[b] [S,C]
+  int nb, L, S, tiles_per_batch;
+  const uint8_t* mask0;
+  const uint8_t* mask1;
+  float inv_c, temperature, thr_log;
+  float2* rowpart;   // [nb*L][row_parts]
+  float2* colpart;   // [nb*S][col_parts]
+  int row_parts, col_parts;
+  const float2* rowstat;
+  const float2* colstat;
+  unsigned long long* rowbest;
+  unsigned int* colbest;
 };
+
+enum { EPI_STORE = 0, EPI_CORR_STATS = 1, EPI_CORR_CONF = 2 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,9 +175,13 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
   TileCoord c;
+  c.img = 0; c.oh0 = 0; c.ow0 = 0;
+  if (p.nb > 1) {  // batched row problems (coarse matching): t -> (batch, m_tile, n_tile)
+    c.img = t / p.tiles_per_batch;
+    t -= c.img * p.tiles_per_batch;
+  }
   c.m_tile = t / p.n_tiles;
   c.n_tile = t - c.m_tile * p.n_tiles;
-  c.img = 0; c.oh0 = 0; c.ow0 = 0;
   if (p.mode == 1) {
     c.img = c.m_tile / p.tiles_per_img;
     int r = c.m_tile - c.img * p.tiles_per_img;
@@ -175,6 +193,25 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
 }
 
 // ------------------------------------------------------------------------------------------- kernel
+// 32-lane "transposing" reduction: on return lane l holds op over all lanes of v[l] (31 shuffles for 32 values).
+template <class Op>
+__device__ __forceinline__ float transpose_reduce(float (&v)[32], int lane, Op op) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const float send = up ? v[k] : v[k + s];
+      const float keep = up ? v[k + s] : v[k];
+      v[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, s));
+    }
+  }
+  return v[0];
+}
+struct OpMax { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpAdd { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
+
+template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ TMaps maps, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -240,8 +277,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             const int m0 = tc.m_tile * BM;
             if (kb < p.cb1) {
               bk = kb * BK;
-              tma_load_3d(sA, &maps.a_hi[0], fb, kb * BK, m0, 0);
-              tma_load_3d(sA + A_TILE_BYTES, &maps.a_lo[0], fb, kb * BK, m0, 0);
+              tma_load_3d(sA, &maps.a_hi[0], fb, kb * BK, m0, tc.img);
+              tma_load_3d(sA + A_TILE_BYTES, &maps.a_lo[0], fb, kb * BK, m0, tc.img);
             } else {
               const int k2 = (kb - p.cb1) * BK;
               bk = p.K1 + k2;
@@ -262,9 +299,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             tma_load_4d(sA, &maps.a_hi[view], fb, cb * BK, tc.ow0 + dw, tc.oh0 + dh, tc.img);
             tma_load_4d(sA + A_TILE_BYTES, &maps.a_lo[view], fb, cb * BK, tc.ow0 + dw, tc.oh0 + dh, tc.img);
           }
-          tma_load_3d(sB, &maps.b_h8, fb, bk, n0, 0);
-          tma_load_3d(sB + b_plane, &maps.b_lo, fb, bk, n0, 0);
-          tma_load_3d(sB + 2 * b_plane, &maps.b_hi, fb, bk, n0, 0);
+          const int bb = (p.mode == 0) ? tc.img : 0;  // weights: one matrix; coarse matching: f1 of the same pair
+          tma_load_3d(sB, &maps.b_h8, fb, bk, n0, bb);
+          tma_load_3d(sB + b_plane, &maps.b_lo, fb, bk, n0, bb);
+          tma_load_3d(sB + 2 * b_plane, &maps.b_hi, fb, bk, n0, bb);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -327,13 +365,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       if (p.mode == 0) {
         row = (long long)tc.m_tile * BM + r_in_tile;
         row_ok = row < p.M;
+        if (EPI != EPI_STORE) row += (long long)tc.img * p.L;  // global row of the batched problem
       } else {
         const int oh = tc.oh0 + r_in_tile / TW, ow = tc.ow0 + r_in_tile % TW;
         row_ok = oh < p.OH && ow < p.OW;
         row = ((long long)tc.img * p.OH + oh) * p.OW + ow;
       }
       float rmask = 1.f;
-      if (p.row_mask && row_ok) rmask = (float)p.row_mask[row];
+      if (EPI == EPI_STORE && p.row_mask && row_ok) rmask = (float)p.row_mask[row];
 
       // ---- drain the chunk accumulators into fp32 registers (round-to-nearest adds)
       float acc[4][32];
@@ -360,6 +399,85 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(buf));
+      }
+
+      // ---- coarse-matching sweeps (networks/loftr/utils/coarse_matching.py:111-118, 174-190)
+      if constexpr (EPI == EPI_CORR_STATS) {
+        const bool rmasked = p.mask0 && row_ok && p.mask0[row] == 0;
+        float rm = -INFINITY, rs = 0.f;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          const int c0 = (gi * 2 + half) * 32;
+          if (c0 >= p.bn) continue;           // warp-uniform
+          const int cbase = n0 + c0;
+          float v[32];
+          float gm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + j;
+            float x = __fdiv_rn(acc[gi][j] * (1.f / kSplitScale) * p.inv_c, p.temperature);
+            const bool cmasked = p.mask1 && c < p.S && p.mask1[(long long)tc.img * p.S + c] == 0;
+            if (rmasked || cmasked) x = -1e9f;
+            if (c >= p.S || !row_ok) x = -INFINITY;
+            v[j] = x;
+            gm = fmaxf(gm, x);
+          }
+          // row partial (softmax over dim 2): online (max, sum exp) over this thread's columns
+          if (gm > rm) { rs *= __expf(rm - gm); rm = gm; }
+          if (rm > -INFINITY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rs += __expf(v[j] - rm);
+          }
+          // column partial (softmax over dim 1) over the 32 rows of this warp
+          float w[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[j] = v[j];
+          const float cm = transpose_reduce(w, lane, OpMax());
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float cmj = __shfl_sync(0xffffffffu, cm, j);
+            w[j] = (v[j] > -INFINITY) ? __expf(v[j] - cmj) : 0.f;
+          }
+          const float cs = transpose_reduce(w, lane, OpAdd());
+          const int c = cbase + lane;
+          if (c < p.S)
+            p.colpart[((long long)tc.img * p.S + c) * p.col_parts + tc.m_tile * 4 + q] = make_float2(cm, cs);
+        }
+        if (row_ok) p.rowpart[row * p.row_parts + tc.n_tile * 2 + half] = make_float2(rm, rs);
+        continue;
+      }
+      if constexpr (EPI == EPI_CORR_CONF) {
+        if (!row_ok) continue;
+        const bool rmasked = p.mask0 && p.mask0[row] == 0;
+        const float2 rst = p.rowstat[row];
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          const int c0 = (gi * 2 + half) * 32;
+          if (c0 >= p.bn) continue;
+          const int cbase = n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + j;
+            if (c >= p.S) continue;
+            const long long gc = (long long)tc.img * p.S + c;
+            float x = __fdiv_rn(acc[gi][j] * (1.f / kSplitScale) * p.inv_c, p.temperature);
+            if (rmasked || (p.mask1 && p.mask1[gc] == 0)) x = -1e9f;
+            const float2 cst = __ldg(&p.colstat[gc]);
+            // conf = softmax_col * softmax_row <= exp((x - rmax) + (x - cmax)): only entries that can exceed the
+            // threshold are evaluated exactly; all others can never be a match (coarse_matching.py:174-190)
+            const float t = (x - rst.x) + (x - cst.x);
+            if (t > p.thr_log) {
+              const float conf = __fdiv_rn(expf(x - cst.x), cst.y) * __fdiv_rn(expf(x - rst.x), rst.y);
+              const unsigned int bits = __float_as_uint(conf);
+              const unsigned long long pk = ((unsigned long long)bits << 32) | (unsigned long long)(~(unsigned int)c);
+              best = pk > best ? pk : best;
+              atomicMax(&p.colbest[gc], bits);
+            }
+          }
+        }
+        if (best) atomicMax(&p.rowbest[row], best);
+        continue;
       }
 
       // ---- final epilogue from registers
@@ -487,8 +605,9 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, co
   return 0;
 }
 
-int rows_map(CUtensorMap* m, const __half* ptr, uint64_t K, uint64_t rows, uint64_t ld, uint32_t box_rows) {
-  uint64_t dims[3] = {K, rows, 1};
+int rows_map(CUtensorMap* m, const __half* ptr, uint64_t K, uint64_t rows, uint64_t ld, uint32_t box_rows,
+             uint64_t nbatch = 1) {
+  uint64_t dims[3] = {K, rows, nbatch};
   uint64_t strides[2] = {ld * 2, rows * ld * 2};
   uint32_t box[3] = {BK, box_rows, 1};
   return make_map(m, ptr, 3, dims, strides, box);
@@ -586,14 +705,73 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   p.act0 = g.act0; p.act1 = g.act1; p.act_split = g.act_split; p.div = g.div;
   p.out_f32 = g.out_f32; p.out_hi = g.out.hi; p.out_lo = g.out.lo; p.out_h8 = g.out.h8; p.ldp = g.out.ld;
 
+  p.nb = 1;
   const int smem = p.stages * p.stage_bytes + 1024 + 512;
   static bool attr_done = false;
   if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = std::min(p.num_tiles, ctx.sm_count);
-  umma_gemm_kernel<<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+  umma_gemm_kernel<EPI_STORE><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+  ctx.launches++;
+  GIMB_LAUNCH_CHECK();
+  return 0;
+}
+
+void umma_corr_parts(int L, int S, int* row_parts, int* col_parts) {
+  *row_parts = cdiv(S, 256) * 2;
+  *col_parts = cdiv(L, BM) * 4;
+}
+
+int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
+  GIMB_CHECK(c.f0.hi && c.f0.lo && c.f1.hi && c.f1.lo && c.f1.h8, "umma_corr: operand planes missing");
+  GIMB_CHECK(c.C % 32 == 0, "umma_corr: C must be a multiple of 32");
+  if (ctx.dry || c.N == 0) return 0;
+  KParams p = {};
+  TMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.mode = 0;
+  p.N = c.S;
+  p.n_tiles = cdiv(c.S, 256);
+  p.bn = 256;
+  if (c.S < 256) p.bn = cdiv(c.S, 16) * 16;
+  p.K1 = c.C; p.cb1 = c.C / BK; p.cb2 = 0; p.num_kb = p.cb1;
+  p.KH = p.KW = 1; p.stride = 1; p.pad = 0;
+  p.M = c.L;
+  const int m_tiles = cdiv(c.L, BM);
+  p.nb = c.N; p.L = c.L; p.S = c.S;
+  p.tiles_per_batch = m_tiles * p.n_tiles;
+  p.num_tiles = c.N * p.tiles_per_batch;
+  GIMB_TRY(rows_map(&maps.a_hi[0], c.f0.hi, c.C, c.L, c.f0.ld, BM, c.N));
+  GIMB_TRY(rows_map(&maps.a_lo[0], c.f0.lo, c.C, c.L, c.f0.ld, BM, c.N));
+  GIMB_TRY(rows_map(&maps.b_h8, c.f1.h8, c.C, c.S, c.f1.ld, p.bn, c.N));
+  GIMB_TRY(rows_map(&maps.b_lo, c.f1.lo, c.C, c.S, c.f1.ld, p.bn, c.N));
+  GIMB_TRY(rows_map(&maps.b_hi, c.f1.hi, c.C, c.S, c.f1.ld, p.bn, c.N));
+  p.stage_bytes = 2 * A_TILE_BYTES + 3 * p.bn * BK * 2;
+  p.stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes));
+  p.num_chunks = cdiv(p.num_kb, CHUNK_KB);
+  p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+  p.mask0 = c.mask0; p.mask1 = c.mask1;
+  p.inv_c = 1.f / (float)c.C;
+  p.temperature = c.temperature;
+  p.thr_log = c.thr > 0.f ? logf(c.thr) - 1e-3f : -INFINITY;
+  p.rowpart = c.rowpart; p.colpart = c.colpart;
+  umma_corr_parts(c.L, c.S, &p.row_parts, &p.col_parts);
+  p.rowstat = c.rowstat; p.colstat = c.colstat; p.rowbest = c.rowbest; p.colbest = c.colbest;
+  // the multiplexing TMA batch coordinate is tile.img for both operands (mode 0)
+  const int smem = p.stages * p.stage_bytes + 1024 + 512;
+  static bool attr_done = false;
+  if (!attr_done) {
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_done = true;
+  }
+  const int grid = std::min(p.num_tiles, ctx.sm_count);
+  if (pass == 0)
+    umma_gemm_kernel<EPI_CORR_STATS><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+  else
+    umma_gemm_kernel<EPI_CORR_CONF><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;

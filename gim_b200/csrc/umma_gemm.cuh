@@ -51,6 +51,25 @@ struct UmmaGemm {
 
 int umma_gemm(Ctx& ctx, const UmmaGemm& g);
 
+// Coarse-matching correlation sweeps on the tensor cores (networks/loftr/utils/coarse_matching.py:111-118):
+// pass 0 = per-tile softmax statistics (row / column partial (max, sum exp)), pass 1 = confidence + mutual-NN maxima.
+struct UmmaCorr {
+  SplitPlanes f0;   // [N*L, C] (hi, lo)
+  SplitPlanes f1;   // [N*S, C] (hi, lo, h8)
+  int N = 0, L = 0, S = 0, C = 0;
+  const uint8_t* mask0 = nullptr;
+  const uint8_t* mask1 = nullptr;
+  float temperature = 0.1f, thr = 0.2f;
+  float2* rowpart = nullptr;   // [N*L][row_parts]
+  float2* colpart = nullptr;   // [N*S][col_parts]
+  const float2* rowstat = nullptr;
+  const float2* colstat = nullptr;
+  unsigned long long* rowbest = nullptr;
+  unsigned int* colbest = nullptr;
+};
+void umma_corr_parts(int L, int S, int* row_parts, int* col_parts);
+int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass);
+
 // fp32 -> split planes (weights at load time; test helper)
 int split_planes(Ctx& ctx, const float* src, int64_t rows, int cols, int src_ld, const SplitPlanes& dst);
 
