@@ -1,0 +1,62 @@
+"""world_size-2 gloo test of the pair sharding + end-of-loop gather (no GPU, no data-path collective)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gim_b200 import dist as gdist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_pairs, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = gdist.shard_range(n_pairs, rank, world)
+    # fake per-pair results: pair k yields (k % 5) matches
+    rows = []
+    for k in range(lo, hi):
+        m = k % 5
+        data = {"m_bids": torch.zeros(m, dtype=torch.int64), "mkpts0_f": torch.full((m, 2), float(k)),
+                "mkpts1_f": torch.full((m, 2), float(k) + 0.5), "mconf": torch.full((m,), 0.25)}
+        rows.append(gdist.pack_matches([k], data))
+    rows = torch.cat(rows, 0) if rows else torch.zeros(0, 6)
+    counts = gdist.gather_counts(rows.shape[0])
+    allrows = gdist.gather_rows(rows, dst=0)
+    if rank == 0:
+        torch.save({"counts": counts, "rows": allrows}, out)
+    dist.destroy_process_group()
+
+
+def test_shard_range_is_a_partition():
+    for n in (0, 1, 7, 32, 45916):
+        for w in (1, 2, 4, 8):
+            spans = [gdist.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gather(tmp_path):
+    out = str(tmp_path / "res.pt")
+    n_pairs = 11
+    mp.spawn(_worker, args=(2, _free_port(), n_pairs, out), nprocs=2, join=True)
+    res = torch.load(out)
+    expect = sum(k % 5 for k in range(n_pairs))
+    assert sum(res["counts"]) == expect and len(res["counts"]) == 2
+    rows = res["rows"]
+    assert rows.shape == (expect, 6)
+    # rank order == pair order, no duplicates, every pair present with its match count
+    ids = rows[:, 0].long()
+    assert torch.equal(ids, torch.sort(ids).values)
+    for k in range(n_pairs):
+        assert int((ids == k).sum()) == k % 5
