@@ -1,6 +1,8 @@
 // test_hooks.cu - C entry points used only by tests/: run one GEMM-shaped layer through the tcgen05 kernel
 // and through the fp32 CUDA-core kernel on the same device buffers, so the two can be compared with a
 // float64 reference on the host side.
+#include <vector>
+
 #include "../../include/gimb200.h"
 #include "ops.cuh"
 #include "umma_gemm.cuh"
@@ -88,4 +90,66 @@ extern "C" int gimb_test_conv(const float* in, const float* in2, int B, int H, i
     GIMB_LAUNCH_CHECK();
   }
   return 0;
+}
+
+// Times the tcgen05 GEMM alone on one layer shape (operands pre-split, buffers allocated here, zero data except a
+// constant fill): `iters` back-to-back launches between two CUDA events on `stream`.  flags: 1 = folded BN,
+// 2 = residual, 4 = fp32 output, 8 = fp16-plane output.
+extern "C" int gimb_bench_layer(int B, int H, int W, int C1, int C2, int Cout, int ksize, int stride, int flags, int act,
+                                int iters, float* ms_out, void* stream) {
+  GIMB_CHECK(ms_out && iters > 0, "gimb_bench_layer: bad argument");
+  Ctx ctx;
+  ctx.stream = (cudaStream_t)stream;
+  int dev = 0;
+  GIMB_CUDA(cudaGetDevice(&dev));
+  GIMB_CUDA(cudaDeviceGetAttribute(&ctx.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  const int pad = ksize / 2;
+  const int OH = (H + 2 * pad - ksize) / stride + 1, OW = (W + 2 * pad - ksize) / stride + 1;
+  const long long M = (long long)B * OH * OW, pix = (long long)B * H * W;
+  const int Cin = C1 + C2;
+  auto pitch8 = [](int v) { return (v + 7) / 8 * 8; };
+  std::vector<void*> bufs;
+  auto dalloc = [&](size_t bytes, int fill) -> void* {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    cudaMemset(p, fill, bytes);
+    bufs.push_back(p);
+    return p;
+  };
+  SplitPlanes a, a2, b, o;
+  a.ld = pitch8(C1);
+  a.hi = (__half*)dalloc(pix * a.ld * 2, 0x3c); a.lo = (__half*)dalloc(pix * a.ld * 2, 0);
+  if (C2) { a2.ld = pitch8(C2); a2.hi = (__half*)dalloc(pix * a2.ld * 2, 0x3c); a2.lo = (__half*)dalloc(pix * a2.ld * 2, 0); }
+  const int taps = ksize * ksize, ldk = pitch8(Cin);
+  b.ld = taps * ldk;
+  b.hi = (__half*)dalloc((size_t)Cout * b.ld * 2, 0x1c); b.lo = (__half*)dalloc((size_t)Cout * b.ld * 2, 0);
+  b.h8 = (__half*)dalloc((size_t)Cout * b.ld * 2, 0x1c);
+  float* scale = (flags & 1) ? (float*)dalloc(Cout * 4, 0) : nullptr;
+  float* bias = (flags & 1) ? (float*)dalloc(Cout * 4, 0) : nullptr;
+  float* res = (flags & 2) ? (float*)dalloc(M * Cout * 4, 0) : nullptr;
+  float* of = (flags & 4) ? (float*)dalloc(M * Cout * 4, 0) : nullptr;
+  if (flags & 8) { o.ld = pitch8(Cout); o.hi = (__half*)dalloc(M * o.ld * 2, 0); o.lo = (__half*)dalloc(M * o.ld * 2, 0); }
+  int rc = 0;
+  for (void* p : bufs) if (!p) rc = 1;
+  if (rc) { for (void* p : bufs) if (p) cudaFree(p); set_error("gimb_bench_layer: out of memory"); return 1; }
+  UmmaGemm g;
+  g.a = a; g.a2 = a2; g.b = b; g.N = Cout;
+  if (ksize == 1 && stride == 1) { g.mode = 0; g.M = M; g.K1 = C1; g.K2 = C2; }
+  else { g.mode = 1; g.K1 = Cin; g.B = B; g.H = H; g.W = W; g.KH = g.KW = ksize; g.stride = stride; g.pad = pad; g.OH = OH; g.OW = OW; g.ldk = ldk; }
+  g.scale = scale; g.bias = bias; g.residual = res; g.act0 = g.act1 = act; g.out_f32 = of; g.out = o;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  rc = umma_gemm(ctx, g);  // warm-up
+  if (!rc) {
+    cudaEventRecord(e0, ctx.stream);
+    for (int i = 0; i < iters && !rc; ++i) rc = umma_gemm(ctx, g);
+    cudaEventRecord(e1, ctx.stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("gimb_bench_layer: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / iters;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (void* p : bufs) cudaFree(p);
+  return rc;
 }

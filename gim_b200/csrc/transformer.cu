@@ -69,22 +69,29 @@ constexpr int KV_STRIDE = 32 * 32 + 32;      // floats per (b, h) result
 
 __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict__ kv, int S, int C, int nhead,
                                                          int nsplit, float* __restrict__ part) {
-  __shared__ float Ks[KV_CHUNK][33];
-  __shared__ float Vs[KV_CHUNK][32];
+  // 256 threads = 4 row-subsets x (8 d-quads x 8 v-quads): each thread owns a 4 x 4 block of KV[d][v] for the rows
+  // r = sub (mod 4) of every staged chunk; the four subsets are summed through shared memory in a fixed order.
+  __shared__ __align__(16) float Ks[KV_CHUNK][32];
+  __shared__ __align__(16) float Vs[KV_CHUNK][32];
+  __shared__ float red[3][32 * 32 + 32];
   const int bh = blockIdx.x, split = blockIdx.y;
   const int b = bh / nhead, h = bh - b * nhead;
   const int tid = threadIdx.x;
-  const int d = tid >> 3, v0 = (tid & 7) * 4;
+  const int sub = tid >> 6, dq = (tid & 63) >> 3, vq = tid & 7;
   const int per = (S + nsplit - 1) / nsplit;
   const int s_begin = split * per, s_end = min(S, s_begin + per);
   const float* base = kv + (size_t)b * S * 2 * C;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float ksum = 0.f;
+  float acc[4][4];
+  float ksum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int s0 = s_begin; s0 < s_end; s0 += KV_CHUNK) {
     // 32 rows x (32 K + 32 V) floats = 512 float4: 2 per thread
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      int idx = tid + i * 256;       // 0..511
+      int idx = tid + i * 256;
       int r = idx >> 4, q4 = idx & 15;  // row, float4 index (0..7 -> K, 8..15 -> V)
       int s = s0 + r;
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -92,28 +99,54 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict
         const float* rowp = base + (size_t)s * 2 * C + (q4 < 8 ? h * 32 + q4 * 4 : C + h * 32 + (q4 - 8) * 4);
         t = *reinterpret_cast<const float4*>(rowp);
       }
-      if (q4 < 8) {
-        Ks[r][q4 * 4 + 0] = t.x; Ks[r][q4 * 4 + 1] = t.y; Ks[r][q4 * 4 + 2] = t.z; Ks[r][q4 * 4 + 3] = t.w;
-      } else {
-        *reinterpret_cast<float4*>(&Vs[r][(q4 - 8) * 4]) = t;
+      if (q4 < 8) *reinterpret_cast<float4*>(&Ks[r][q4 * 4]) = t;
+      else *reinterpret_cast<float4*>(&Vs[r][(q4 - 8) * 4]) = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = sub; r < KV_CHUNK; r += 4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(&Ks[r][dq * 4]);
+      const float4 v4 = *reinterpret_cast<const float4*>(&Vs[r][vq * 4]);
+      const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(kk[i], vv[j], acc[i][j]);
+        ksum[i] += kk[i];
       }
     }
     __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < KV_CHUNK; ++r) {
-      float k = Ks[r][d];
-      float4 vv = *reinterpret_cast<const float4*>(&Vs[r][v0]);
-      acc[0] = fmaf(k, vv.x, acc[0]);
-      acc[1] = fmaf(k, vv.y, acc[1]);
-      acc[2] = fmaf(k, vv.z, acc[2]);
-      acc[3] = fmaf(k, vv.w, acc[3]);
-      ksum += k;
-    }
-    __syncthreads();
   }
-  float* o = part + ((size_t)bh * nsplit + split) * KV_STRIDE;
-  *reinterpret_cast<float4*>(o + d * 32 + v0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  if ((tid & 7) == 0) o[1024 + d] = ksum;
+  // fixed-order reduction over the 4 row subsets
+  if (sub > 0) {
+    float* rp = red[sub - 1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rp[(dq * 4 + i) * 32 + vq * 4 + j] = acc[i][j];
+      if (vq == 0) rp[1024 + dq * 4 + i] = ksum[i];
+    }
+  }
+  __syncthreads();
+  if (sub == 0) {
+    float* o = part + ((size_t)bh * nsplit + split) * KV_STRIDE;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 r4;
+      float* rr = &r4.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = (dq * 4 + i) * 32 + vq * 4 + j;
+        rr[j] = ((acc[i][j] + red[0][e]) + red[1][e]) + red[2][e];
+      }
+      *reinterpret_cast<float4*>(o + (dq * 4 + i) * 32 + vq * 4) = r4;
+      if (vq == 0) {
+        const int e = 1024 + dq * 4 + i;
+        o[e] = ((ksum[i] + red[0][e]) + red[1][e]) + red[2][e];
+      }
+    }
+  }
 }
 
 // step 2: fixed-order reduction of the partials -> kvf[bh][1056]
@@ -127,34 +160,49 @@ __global__ void kv_reduce_kernel(const float* __restrict__ part, int nsplit, flo
 }
 
 // step 3: msg[l, h*32+v] = (sum_d Q'[l,h,d] KV[h,d,v]) * (1 / (sum_d Q'[l,h,d] Ksum[h,d] + eps)) * S
-// one CTA = 8 warps, each warp walks rows; KV of all heads of image b lives in shared memory.
+// 256 threads = 8 heads x 32 value channels; each thread keeps its KV column and the head's Ksum in registers
+// and streams rows of Q' from shared memory (float4 broadcast reads): 64 FFMA per 8 LDS.128.
+constexpr int AP_ROWS = 32;
 __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ q, const float* __restrict__ kvf,
                                                          int L, int C, int nhead, float vlen, int rows_per_cta,
                                                          float* __restrict__ msg, const PlanesDev sp) {
-  extern __shared__ float sm[];  // [nhead][KV_STRIDE]
+  __shared__ __align__(16) float Qs[AP_ROWS][256];
   const int b = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < nhead * KV_STRIDE; i += 256) sm[i] = kvf[(size_t)b * nhead * KV_STRIDE + i];
-  __syncthreads();
+  const int tid = threadIdx.x, v = tid & 31, h = tid >> 5;
+  float kvr[32], ksr[32];
+  {
+    const float* kvh = kvf + ((size_t)b * nhead + h) * KV_STRIDE;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) { kvr[d] = kvh[d * 32 + v]; ksr[d] = kvh[1024 + d]; }
+  }
   const int l0 = blockIdx.x * rows_per_cta;
   const int l1 = min(L, l0 + rows_per_cta);
-  for (int l = l0 + warp; l < l1; l += 8) {
-    const float* qr = q + ((size_t)b * L + l) * C;
-    const size_t grow = (size_t)b * L + l;
-    for (int h = 0; h < nhead; ++h) {
-      const float* kvh = sm + h * KV_STRIDE;
-      float qv = qr[h * 32 + lane];
-      float zden = warp_sum(qv * kvh[1024 + lane]);
-      float o = 0.f;
+  for (int lc = l0; lc < l1; lc += AP_ROWS) {
+    const int nr = min(AP_ROWS, l1 - lc);
+    __syncthreads();
+    for (int i = tid; i < nr * 64; i += 256) {
+      const int r = i >> 6, c4 = i & 63;
+      *reinterpret_cast<float4*>(&Qs[r][c4 * 4]) =
+          *reinterpret_cast<const float4*>(q + ((size_t)b * L + lc + r) * C + c4 * 4);
+    }
+    __syncthreads();
+    for (int r = 0; r < nr; ++r) {
+      float o = 0.f, z = 0.f;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) o = fmaf(__shfl_sync(0xffffffffu, qv, d), kvh[d * 32 + lane], o);
-      float z = 1.f / (zden + 1e-6f);
-      const float r = o * z * vlen;
-      if (msg) msg[grow * C + h * 32 + lane] = r;
+      for (int d4 = 0; d4 < 8; ++d4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&Qs[r][h * 32 + d4 * 4]);
+        o = fmaf(q4.x, kvr[d4 * 4 + 0], o); z = fmaf(q4.x, ksr[d4 * 4 + 0], z);
+        o = fmaf(q4.y, kvr[d4 * 4 + 1], o); z = fmaf(q4.y, ksr[d4 * 4 + 1], z);
+        o = fmaf(q4.z, kvr[d4 * 4 + 2], o); z = fmaf(q4.z, ksr[d4 * 4 + 2], z);
+        o = fmaf(q4.w, kvr[d4 * 4 + 3], o); z = fmaf(q4.w, ksr[d4 * 4 + 3], z);
+      }
+      const float res = o * (1.f / (z + 1e-6f)) * vlen;
+      const size_t grow = (size_t)b * L + lc + r;
+      if (msg) msg[grow * C + tid] = res;
       if (sp.hi) {
-        const __half hh = __float2half_rn(r);
-        sp.hi[grow * sp.ld + h * 32 + lane] = hh;
-        sp.lo[grow * sp.ld + h * 32 + lane] = __float2half_rn((r - __half2float(hh)) * kSplitScale);
+        const __half hh = __float2half_rn(res);
+        sp.hi[grow * sp.ld + tid] = hh;
+        sp.lo[grow * sp.ld + tid] = __float2half_rn((res - __half2float(hh)) * kSplitScale);
       }
     }
   }
@@ -253,9 +301,9 @@ int linear_attention(Ctx& ctx, const float* q, const float* kv, int B, int L, in
     int total = BH * KV_STRIDE;
     kv_reduce_kernel<<<cdiv(total, 256), 256, 0, ctx.stream>>>(part, nsplit, kvf, total);
     GIMB_LAUNCH_CHECK();
-    const int rows_per_cta = 64;
-    size_t smem = (size_t)nhead * KV_STRIDE * sizeof(float);
-    attn_apply_kernel<<<dim3(cdiv(L, rows_per_cta), B), 256, smem, ctx.stream>>>(q, kvf, L, C, nhead, (float)S,
+    const int rows_per_cta = 128;
+    GIMB_CHECK(C == 256 && nhead == 8, "linear_attention: coarse flavour is built for C = 256, 8 heads");
+    attn_apply_kernel<<<dim3(cdiv(L, rows_per_cta), B), 256, 0, ctx.stream>>>(q, kvf, L, C, nhead, (float)S,
                                                                                    rows_per_cta, msg, sp);
     GIMB_LAUNCH_CHECK();
     ctx.launches += 3;

@@ -15,6 +15,8 @@
 //
 // Tile: BM = 128 output rows (mode 0: consecutive rows; mode 1: an 8 x 16 pixel patch of one image),
 //       BN = whole N up to 256 (rounded to 16), BK = 32 fp16 (64-byte rows).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "ops.cuh"
@@ -31,8 +33,9 @@ constexpr int MAX_STAGES = 8;
 constexpr int NUM_EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each owning alternate 32-column groups
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;  // warpgroup 0: TMA, MMA, 2 idle warps; warpgroups 1-2: epilogue
 constexpr int REGS_LOW = 40, REGS_HIGH = 232;           // setmaxnreg split: 4*32*40 + 8*32*232 = 64512 <= 65536
-constexpr int CHUNK_KB = 2;        // k-blocks (of 32) accumulated inside the tensor core before the fp32 (RN) drain
+constexpr int CHUNK_KB_DEFAULT = 2;  // k-blocks (of 32) accumulated inside the tensor core before the fp32 (RN) drain
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_EXTRA = 1024 /*alignment slack*/ + 512 /*barriers*/ + NUM_EPI_WARPS * 32 * 33 * 4 /*transpose tiles*/;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 
@@ -51,7 +54,7 @@ struct KParams {
   int ldk;
   int N, n_tiles, bn;
   int stages, stage_bytes;
-  int num_tiles, num_kb, num_chunks;
+  int num_tiles, num_kb, num_chunks, chunk_kb;
   unsigned idesc;
   const float* scale;
   const float* bias;
@@ -211,7 +214,191 @@ __device__ __forceinline__ float transpose_reduce(float (&v)[32], int lane, Op o
 struct OpMax { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
 struct OpAdd { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
 
-template <int EPI>
+// ---- store epilogue of one 32 x 32 block: lane = output column, fully unrolled walk over the warp's 32 rows.
+// Row rr of the warp maps to global row g0 + (rr >> 4) * rowjump + (rr & 15) (mode 0: rowjump = 16, i.e. g0 + rr;
+// mode 1: two 16-pixel runs of the 8 x 16 patch, rowjump = OW).  Everything row-invariant is hoisted; the residual
+// block is prefetched into registers (32 independent coalesced loads in flight) before it is consumed.
+enum { OUT_F32 = 1, OUT_PLANES = 2, OUT_RESIDUAL = 4 };
+
+template <int OUT, bool kSlowAct>
+__device__ __forceinline__ void store_rows(const KParams& p, const float* tb, int lane, int c, bool c_ok, long long g0,
+                                           long long rowjump, unsigned valid, unsigned rmask_bits) {
+  // Three straight-line phases (loads, math, stores) over all 32 rows with no branches inside, so the 32 independent
+  // row chains overlap instead of executing one after another (the branchy per-row form ran ~200 cycles per row).
+  const float sc = (p.scale && c_ok) ? __ldg(p.scale + c) * (1.f / kSplitScale) : (1.f / kSplitScale);
+  const float bi = (p.scale && c_ok) ? __ldg(p.bias + c) : 0.f;
+  const int act = c >= p.act_split ? p.act1 : p.act0;
+  const bool is_relu = act == ACT_RELU, is_leaky = act == ACT_LEAKY;
+  const bool plane_col = (OUT & OUT_PLANES) && c < p.ldp;
+  const bool has_res = (OUT & OUT_RESIDUAL) && p.residual != nullptr;
+  const float div = p.div;
+  float* const of = p.out_f32;
+  __half* const ohi = p.out_hi;
+  __half* const olo = p.out_lo;
+  const long long n64 = p.N, ld64 = p.ldp;
+  float v[32];
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) v[rr] = tb[rr * 33 + lane];
+  if (has_res) {
+    float res[32];
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      const long long grow = g0 + (rr >> 4) * rowjump + (rr & 15);
+      res[rr] = (c_ok && ((valid >> rr) & 1u)) ? __ldg(p.residual + grow * n64 + c) : 0.f;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) v[rr] = fmaf(v[rr], sc, bi) + res[rr];
+  } else {
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) v[rr] = fmaf(v[rr], sc, bi);
+  }
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    float x = v[rr];
+    if (kSlowAct) {
+      if (act == ACT_ELU1) x = x > 0.f ? x + 1.f : expf(x);
+      else if (act == ACT_DIVS) x = __fdiv_rn(x, div);
+      else if (is_relu) x = fmaxf(x, 0.f);
+      else if (is_leaky) x = fmaxf(x, 0.01f * x);
+      if (!((rmask_bits >> rr) & 1u)) x = 0.f;
+    } else {
+      const float r = fmaxf(x, 0.f), l = fmaxf(x, 0.01f * x);
+      x = is_relu ? r : (is_leaky ? l : x);
+    }
+    v[rr] = x;
+  }
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    const bool ok = (valid >> rr) & 1u;
+    const long long grow = g0 + (rr >> 4) * rowjump + (rr & 15);
+    if ((OUT & OUT_F32) && ok && c_ok) of[grow * n64 + c] = v[rr];
+    if (OUT & OUT_PLANES) {
+      const float x = c_ok ? v[rr] : 0.f;  // pad channels of the fp16 planes are zero
+      const __half h = __float2half_rn(x);
+      const __half l = __float2half_rn((x - __half2float(h)) * kSplitScale);
+      if (ok && plane_col) {
+        ohi[grow * ld64 + c] = h;
+        olo[grow * ld64 + c] = l;
+      }
+    }
+  }
+}
+
+template <int OUT, bool kSlowAct>
+__device__ __forceinline__ void store_group(const KParams& p, const float* tb, int lane, int q, const TileCoord& tc, int cbase) {
+  const int c = cbase + lane;
+  const bool c_ok = c < p.N;
+  long long g0, rowjump;
+  bool my_ok;  // validity of row rr == lane
+  if (p.mode == 0) {
+    g0 = (long long)tc.m_tile * BM + q * 32;
+    rowjump = 16;
+    my_ok = g0 + lane < p.M;
+  } else {
+    const int oh = tc.oh0 + q * 2, ow = tc.ow0;
+    g0 = ((long long)tc.img * p.OH + oh) * p.OW + ow;
+    rowjump = p.OW;
+    my_ok = (oh + (lane >> 4) < p.OH) && (ow + (lane & 15) < p.OW);
+  }
+  const unsigned valid = __ballot_sync(0xffffffffu, my_ok);
+  unsigned rmask_bits = 0xffffffffu;
+  if (kSlowAct && p.row_mask) {  // row masks only occur on the q / kv projections (slow-activation variant)
+    const long long grow = g0 + (lane >> 4) * rowjump + (lane & 15);
+    rmask_bits = __ballot_sync(0xffffffffu, my_ok && p.row_mask[grow] != 0);
+  }
+  store_rows<OUT, kSlowAct>(p, tb, lane, c, c_ok, g0, rowjump, valid, rmask_bits);
+}
+
+// Copy one of the four register-resident 32-column accumulator groups into the warp's smem tile.  The group loop in
+// the epilogues is deliberately NOT unrolled (one copy of the per-group code keeps the SASS small enough for the
+// instruction cache); the switch gives every case static register indices.
+__device__ __forceinline__ void stage_group(float* tb, int lane, const float (&acc)[4][32], int gi) {
+  switch (gi) {
+    case 0:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[0][j];
+      break;
+    case 1:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[1][j];
+      break;
+    case 2:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[2][j];
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[3][j];
+      break;
+  }
+}
+
+// ---- per-group (32 rows x 32 columns per warp) bodies of the coarse-matching epilogues.  `tb` is the warp's
+// padded smem tile holding the raw accumulators row-per-lane: tb[lane * 33 + j] = 2^8 * <f0[row], f1[col j]>.
+__device__ __forceinline__ void corr_stats_group(const KParams& p, float* tb, int lane, int q, int img, int m_tile, int cbase,
+                                              bool row_ok, bool rmasked, float& rm, float& rs) {
+  float* mine = tb + lane * 33;
+  // sim = dot / C / T (same formula as the fp32 sweeps), masked_fill(-1e9), invalid -> -inf; group row max
+  float gm = -INFINITY;
+#pragma unroll 4
+  for (int j = 0; j < 32; ++j) {
+    const int c = cbase + j;
+    float x = __fdiv_rn(mine[j] * (1.f / kSplitScale) * p.inv_c, p.temperature);
+    const bool cmasked = p.mask1 && c < p.S && p.mask1[(long long)img * p.S + c] == 0;
+    if (rmasked || cmasked) x = -1e9f;
+    if (c >= p.S || !row_ok) x = -INFINITY;
+    mine[j] = x;
+    gm = fmaxf(gm, x);
+  }
+  // row partial (softmax over dim 2): online (max, sum exp) over this thread's columns
+  if (gm > rm) { rs *= __expf(rm - gm); rm = gm; }
+  if (rm > -INFINITY) {
+    float a = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) a += __expf(mine[j] - rm);
+    rs += a;
+  }
+  // column partial (softmax over dim 1) over the 32 rows of this warp
+  float v[32], w[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { v[j] = mine[j]; w[j] = v[j]; }
+  const float cm = transpose_reduce(w, lane, OpMax());
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float cmj = __shfl_sync(0xffffffffu, cm, j);
+    w[j] = (v[j] > -INFINITY) ? __expf(v[j] - cmj) : 0.f;
+  }
+  const float cs = transpose_reduce(w, lane, OpAdd());
+  const int c = cbase + lane;
+  if (c < p.S) p.colpart[((long long)img * p.S + c) * p.col_parts + m_tile * 4 + q] = make_float2(cm, cs);
+}
+
+__device__ __forceinline__ void corr_conf_group(const KParams& p, const float* tb, int lane, int img, int cbase, long long row,
+                                             bool rmasked, unsigned long long& best) {
+  const float* mine = tb + lane * 33;
+  const float2 rst = p.rowstat[row];
+#pragma unroll 2
+  for (int j = 0; j < 32; ++j) {
+    const int c = cbase + j;
+    if (c >= p.S) break;
+    const long long gc = (long long)img * p.S + c;
+    float x = __fdiv_rn(mine[j] * (1.f / kSplitScale) * p.inv_c, p.temperature);
+    if (rmasked || (p.mask1 && p.mask1[gc] == 0)) x = -1e9f;
+    const float2 cst = __ldg(&p.colstat[gc]);
+    // conf = softmax_col * softmax_row <= exp((x - rmax) + (x - cmax)): only entries that can exceed the threshold
+    // are evaluated exactly; all others can never be a match (coarse_matching.py:174-190)
+    const float t = (x - rst.x) + (x - cst.x);
+    if (t > p.thr_log) {
+      const float conf = __fdiv_rn(expf(x - cst.x), cst.y) * __fdiv_rn(expf(x - rst.x), rst.y);
+      const unsigned int bits = __float_as_uint(conf);
+      const unsigned long long pk = ((unsigned long long)bits << 32) | (unsigned long long)(~(unsigned int)c);
+      best = pk > best ? pk : best;
+      atomicMax(&p.colbest[gc], bits);
+    }
+  }
+}
+
+template <int EPI, int OUT, bool kSlowAct>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ TMaps maps, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -219,6 +406,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   uint8_t* gen = smem_raw + (base - raw);
   const uint32_t bars = base + p.stages * p.stage_bytes;        // barrier block
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + p.stages * p.stage_bytes + 256);
+  float* tbuf = reinterpret_cast<float*>(gen + p.stages * p.stage_bytes + 512);  // [NUM_EPI_WARPS][32][33] transpose tiles
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
   auto tfull_bar = [&](int b) { return bars + 128u + 8u * b; };
@@ -321,7 +509,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tacc = tmem_base + buf * ACC_COLS;
-          const int kb_end = min(p.num_kb, kb + CHUNK_KB);
+          const int kb_end = min(p.num_kb, kb + p.chunk_kb);
           bool first = true;
           for (; kb < kb_end; ++kb) {
             mbar_wait(full_bar(stage), phase);
@@ -401,143 +589,53 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         if (lane == 0) mbar_arrive(tempty_bar(buf));
       }
 
-      // ---- coarse-matching sweeps (networks/loftr/utils/coarse_matching.py:111-118, 174-190)
+      // ---- coarse-matching sweeps (networks/loftr/utils/coarse_matching.py:111-118, 174-190).
+      // The per-group math lives in __noinline__ functions fed from the warp's smem tile: fully unrolled, the
+      // epilogue was ~100 KB of straight-line SASS and ran instruction-fetch bound (ncu: stalled_no_instructions).
       if constexpr (EPI == EPI_CORR_STATS) {
+        float* tb = tbuf + (warp - 4) * (32 * 33);
         const bool rmasked = p.mask0 && row_ok && p.mask0[row] == 0;
         float rm = -INFINITY, rs = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int gi = 0; gi < 4; ++gi) {
           const int c0 = (gi * 2 + half) * 32;
-          if (c0 >= p.bn) continue;           // warp-uniform
-          const int cbase = n0 + c0;
-          float v[32];
-          float gm = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cbase + j;
-            float x = __fdiv_rn(acc[gi][j] * (1.f / kSplitScale) * p.inv_c, p.temperature);
-            const bool cmasked = p.mask1 && c < p.S && p.mask1[(long long)tc.img * p.S + c] == 0;
-            if (rmasked || cmasked) x = -1e9f;
-            if (c >= p.S || !row_ok) x = -INFINITY;
-            v[j] = x;
-            gm = fmaxf(gm, x);
-          }
-          // row partial (softmax over dim 2): online (max, sum exp) over this thread's columns
-          if (gm > rm) { rs *= __expf(rm - gm); rm = gm; }
-          if (rm > -INFINITY) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) rs += __expf(v[j] - rm);
-          }
-          // column partial (softmax over dim 1) over the 32 rows of this warp
-          float w[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) w[j] = v[j];
-          const float cm = transpose_reduce(w, lane, OpMax());
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float cmj = __shfl_sync(0xffffffffu, cm, j);
-            w[j] = (v[j] > -INFINITY) ? __expf(v[j] - cmj) : 0.f;
-          }
-          const float cs = transpose_reduce(w, lane, OpAdd());
-          const int c = cbase + lane;
-          if (c < p.S)
-            p.colpart[((long long)tc.img * p.S + c) * p.col_parts + tc.m_tile * 4 + q] = make_float2(cm, cs);
+          if (c0 >= p.bn) break;              // warp-uniform
+          __syncwarp();
+          stage_group(tb, lane, acc, gi);
+          corr_stats_group(p, tb, lane, q, tc.img, tc.m_tile, n0 + c0, row_ok, rmasked, rm, rs);
         }
         if (row_ok) p.rowpart[row * p.row_parts + tc.n_tile * 2 + half] = make_float2(rm, rs);
         continue;
       }
       if constexpr (EPI == EPI_CORR_CONF) {
-        if (!row_ok) continue;
-        const bool rmasked = p.mask0 && p.mask0[row] == 0;
-        const float2 rst = p.rowstat[row];
+        float* tb = tbuf + (warp - 4) * (32 * 33);
+        const bool rmasked = p.mask0 && row_ok && p.mask0[row] == 0;
         unsigned long long best = 0ull;
-#pragma unroll
+#pragma unroll 1
         for (int gi = 0; gi < 4; ++gi) {
           const int c0 = (gi * 2 + half) * 32;
-          if (c0 >= p.bn) continue;
-          const int cbase = n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cbase + j;
-            if (c >= p.S) continue;
-            const long long gc = (long long)tc.img * p.S + c;
-            float x = __fdiv_rn(acc[gi][j] * (1.f / kSplitScale) * p.inv_c, p.temperature);
-            if (rmasked || (p.mask1 && p.mask1[gc] == 0)) x = -1e9f;
-            const float2 cst = __ldg(&p.colstat[gc]);
-            // conf = softmax_col * softmax_row <= exp((x - rmax) + (x - cmax)): only entries that can exceed the
-            // threshold are evaluated exactly; all others can never be a match (coarse_matching.py:174-190)
-            const float t = (x - rst.x) + (x - cst.x);
-            if (t > p.thr_log) {
-              const float conf = __fdiv_rn(expf(x - cst.x), cst.y) * __fdiv_rn(expf(x - rst.x), rst.y);
-              const unsigned int bits = __float_as_uint(conf);
-              const unsigned long long pk = ((unsigned long long)bits << 32) | (unsigned long long)(~(unsigned int)c);
-              best = pk > best ? pk : best;
-              atomicMax(&p.colbest[gc], bits);
-            }
-          }
+          if (c0 >= p.bn) break;
+          __syncwarp();
+          stage_group(tb, lane, acc, gi);
+          if (row_ok) corr_conf_group(p, tb, lane, tc.img, n0 + c0, row, rmasked, best);
         }
-        if (best) atomicMax(&p.rowbest[row], best);
+        if (row_ok && best) atomicMax(&p.rowbest[row], best);
         continue;
       }
 
-      // ---- final epilogue from registers
-      if (!row_ok) continue;
-#pragma unroll
+      // ---- final epilogue.  The accumulator arrives row-per-lane (TMEM lane = row); global memory wants
+      // column-per-lane.  Each warp transposes its 32 x 32 block through a private padded smem tile, so every
+      // global access in store_group() is one contiguous 128-byte (fp32) or 64-byte (fp16) segment per warp
+      // instruction.  (Row-per-lane stores cost 32 LSU wavefronts per instruction.)
+      float* tb = tbuf + (warp - 4) * (32 * 33);
+#pragma unroll 1
       for (int gi = 0; gi < 4; ++gi) {
         const int c0 = (gi * 2 + half) * 32;
-        if (c0 >= p.bn) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = acc[gi][j] * (1.f / kSplitScale);
-        const int cbase = n0 + c0;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const int co = cbase + j4 * 4;
-          if (co >= p.N) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = 0.f;
-            continue;
-          }
-          if (p.scale) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + co));
-            const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-            v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], sc.x, bi.x);
-            v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], sc.y, bi.y);
-            v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], sc.z, bi.z);
-            v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], sc.w, bi.w);
-          }
-          if (p.residual) {
-            const float4 rr = *reinterpret_cast<const float4*>(p.residual + row * p.N + co);
-            v[j4 * 4 + 0] += rr.x; v[j4 * 4 + 1] += rr.y; v[j4 * 4 + 2] += rr.z; v[j4 * 4 + 3] += rr.w;
-          }
-          const int act = co >= p.act_split ? p.act1 : p.act0;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = apply_act(v[j4 * 4 + e], act, p.div) * rmask;
-          if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + row * p.N + co) =
-              make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-        }
-        if (p.out_hi) {
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const int co = cbase + j8 * 8;
-            if (co >= p.ldp) continue;
-            __align__(16) __half hi[8];
-            __align__(16) __half lo[8];
-            __align__(16) __half h8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float x = v[j8 * 8 + e];
-              const __half h = __float2half_rn(x);
-              const float hf = __half2float(h);
-              hi[e] = h;
-              lo[e] = __float2half_rn((x - hf) * kSplitScale);
-              h8[e] = __float2half_rn(hf * kSplitScale);
-            }
-            *reinterpret_cast<uint4*>(p.out_hi + row * p.ldp + co) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(p.out_lo + row * p.ldp + co) = *reinterpret_cast<const uint4*>(lo);
-            if (p.out_h8) *reinterpret_cast<uint4*>(p.out_h8 + row * p.ldp + co) = *reinterpret_cast<const uint4*>(h8);
-          }
-        }
+        if (c0 >= p.bn) break;  // warp-uniform
+        __syncwarp();
+        stage_group(tb, lane, acc, gi);
+        __syncwarp();
+        store_group<OUT, kSlowAct>(p, tb, lane, q, tc, n0 + c0);
       }
     }
   }
@@ -603,6 +701,17 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, co
   GIMB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rank %d, dims %llu %llu %llu)", (int)r, rank,
              (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)(rank > 2 ? gd[2] : 0));
   return 0;
+}
+
+// k-blocks per in-TMEM accumulation chunk (GIMB_CHUNK_KB overrides the default for experiments)
+int chunk_kb_setting() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("GIMB_CHUNK_KB");
+    v = e ? atoi(e) : CHUNK_KB_DEFAULT;
+    if (v < 1) v = CHUNK_KB_DEFAULT;
+  }
+  return v;
 }
 
 int rows_map(CUtensorMap* m, const __half* ptr, uint64_t K, uint64_t rows, uint64_t ld, uint32_t box_rows,
@@ -696,24 +805,44 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn));
   }
   p.stage_bytes = 2 * A_TILE_BYTES + 3 * p.bn * BK * 2;
-  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
+  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - SMEM_EXTRA) / p.stage_bytes);
   p.stages = std::max(1, std::min(p.stages, std::max(2, p.num_kb)));
   p.num_tiles = m_tiles * p.n_tiles;
-  p.num_chunks = cdiv(p.num_kb, CHUNK_KB);
+  p.chunk_kb = chunk_kb_setting();
+  p.num_chunks = cdiv(p.num_kb, p.chunk_kb);
   p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
   p.scale = g.scale; p.bias = g.bias; p.residual = g.residual; p.row_mask = g.row_mask;
   p.act0 = g.act0; p.act1 = g.act1; p.act_split = g.act_split; p.div = g.div;
   p.out_f32 = g.out_f32; p.out_hi = g.out.hi; p.out_lo = g.out.lo; p.out_h8 = g.out.h8; p.ldp = g.out.ld;
 
   p.nb = 1;
-  const int smem = p.stages * p.stage_bytes + 1024 + 512;
-  static bool attr_done = false;
-  if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_done = true;
-  }
+  const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
+  const bool slow = g.act0 >= ACT_ELU1 || g.act1 >= ACT_ELU1 || g.row_mask != nullptr;
+  const bool f32 = g.out_f32 != nullptr, planes = g.out.hi != nullptr, res = g.residual != nullptr;
+  GIMB_CHECK(g.out.h8 == nullptr, "umma_gemm: the GEMM epilogue does not produce the h8 plane");
   const int grid = std::min(p.num_tiles, ctx.sm_count);
-  umma_gemm_kernel<EPI_STORE><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+  cudaError_t aerr = cudaSuccess;
+#define GIMB_LAUNCH_VARIANT(OUTV, SLOWV)                                                                          \
+  do {                                                                                                            \
+    static bool done = false;                                                                                     \
+    if (!done) {                                                                                                  \
+      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  SMEM_LIMIT);                                                                    \
+      done = true;                                                                                                \
+    }                                                                                                             \
+    umma_gemm_kernel<EPI_STORE, OUTV, SLOWV><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);                   \
+  } while (0)
+  if (f32 && !planes && !res && slow) GIMB_LAUNCH_VARIANT(OUT_F32, true);
+  else if (f32 && !planes && !res) GIMB_LAUNCH_VARIANT(OUT_F32, false);
+  else if (!f32 && planes && !res && !slow) GIMB_LAUNCH_VARIANT(OUT_PLANES, false);
+  else if (f32 && planes && !slow) GIMB_LAUNCH_VARIANT(OUT_F32 | OUT_PLANES | OUT_RESIDUAL, false);
+  else if (f32 && !planes && res && !slow) GIMB_LAUNCH_VARIANT(OUT_F32 | OUT_RESIDUAL, false);
+  else {
+    set_error("umma_gemm: unsupported epilogue combination (f32=%d planes=%d residual=%d slow_act=%d)", f32, planes, res, slow);
+    return 1;
+  }
+#undef GIMB_LAUNCH_VARIANT
+  GIMB_CUDA(aerr);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;
@@ -749,8 +878,9 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   GIMB_TRY(rows_map(&maps.b_lo, c.f1.lo, c.C, c.S, c.f1.ld, p.bn, c.N));
   GIMB_TRY(rows_map(&maps.b_hi, c.f1.hi, c.C, c.S, c.f1.ld, p.bn, c.N));
   p.stage_bytes = 2 * A_TILE_BYTES + 3 * p.bn * BK * 2;
-  p.stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes));
-  p.num_chunks = cdiv(p.num_kb, CHUNK_KB);
+  p.stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - SMEM_EXTRA) / p.stage_bytes));
+  p.chunk_kb = chunk_kb_setting();
+  p.num_chunks = cdiv(p.num_kb, p.chunk_kb);
   p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
   p.mask0 = c.mask0; p.mask1 = c.mask1;
   p.inv_c = 1.f / (float)c.C;
@@ -760,18 +890,18 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   umma_corr_parts(c.L, c.S, &p.row_parts, &p.col_parts);
   p.rowstat = c.rowstat; p.colstat = c.colstat; p.rowbest = c.rowbest; p.colbest = c.colbest;
   // the multiplexing TMA batch coordinate is tile.img for both operands (mode 0)
-  const int smem = p.stages * p.stage_bytes + 1024 + 512;
+  const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
   static bool attr_done = false;
   if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = std::min(p.num_tiles, ctx.sm_count);
   if (pass == 0)
-    umma_gemm_kernel<EPI_CORR_STATS><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_STATS, 0, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   else
-    umma_gemm_kernel<EPI_CORR_CONF><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_CONF, 0, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;

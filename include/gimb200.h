@@ -162,6 +162,11 @@ int gimb_test_conv(const float* in, const float* in2, int B, int H, int W, int C
                    int act1, int act_split, float div, float* out_umma, float* out_umma_planes,
                    float* out_simt, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Test/bench hook: average device time (ms) of `iters` back-to-back launches of the tcgen05 GEMM on one layer shape
+ * (operands pre-split; flags: 1 = folded BN, 2 = residual, 4 = fp32 output, 8 = fp16-plane output). */
+int gimb_bench_layer(int B, int H, int W, int C1, int C2, int Cout, int ksize, int stride, int flags, int act,
+                     int iters, float* ms_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
