@@ -35,7 +35,8 @@ constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;  // warpgroup 0: TMA, MMA,
 constexpr int REGS_LOW = 40, REGS_HIGH = 232;           // setmaxnreg split: 4*32*40 + 8*32*232 = 64512 <= 65536
 constexpr int CHUNK_KB_DEFAULT = 2;  // k-blocks (of 32) accumulated inside the tensor core before the fp32 (RN) drain
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int SMEM_EXTRA = 1024 /*alignment slack*/ + 512 /*barriers*/ + NUM_EPI_WARPS * 32 * 33 * 4 /*transpose tiles*/;
+constexpr int TBP = 36;  // pitch (floats) of the per-warp 32 x 32 transpose tile: 16-byte aligned rows, conflict-free float4 access
+constexpr int SMEM_EXTRA = 1024 /*alignment slack*/ + 512 /*barriers*/ + NUM_EPI_WARPS * 32 * TBP * 4 /*transpose tiles*/;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 
@@ -71,7 +72,7 @@ struct KParams {
   int nb, L, S, tiles_per_batch;
   const uint8_t* mask0;
   const uint8_t* mask1;
-  float inv_c, temperature, thr_log;
+  float inv_c, temperature, thr_log, sim_scale;
   float2* rowpart;   // [nb*L][row_parts]
   float2* colpart;   // [nb*S][col_parts]
   int row_parts, col_parts;
@@ -220,13 +221,23 @@ struct OpAdd { __device__ __forceinline__ float operator()(float a, float b) con
 // block is prefetched into registers (32 independent coalesced loads in flight) before it is consumed.
 enum { OUT_F32 = 1, OUT_PLANES = 2, OUT_RESIDUAL = 4 };
 
+// Vectorised walk over the warp's 32 x 32 block: lane = (row_sub = lane / 8, column quad = lane % 8); one
+// iteration covers 4 rows x 32 columns with 128-bit accesses (4 contiguous 128-byte row segments per warp
+// instruction), 8 iterations per block.  With 2 epilogue warps per scheduler the epilogue is bound by dependent-
+// issue latency, i.e. by instructions per element: the scalar (lane = column) form needed ~60 per 32 elements.
 template <int OUT, bool kSlowAct>
-__device__ __forceinline__ void store_rows(const KParams& p, const float* tb, int lane, int c, bool c_ok, long long g0,
+__device__ __forceinline__ void store_rows(const KParams& p, const float* tb, int lane, int cbase, long long g0,
                                            long long rowjump, unsigned valid, unsigned rmask_bits) {
-  // Three straight-line phases (loads, math, stores) over all 32 rows with no branches inside, so the 32 independent
-  // row chains overlap instead of executing one after another (the branchy per-row form ran ~200 cycles per row).
-  const float sc = (p.scale && c_ok) ? __ldg(p.scale + c) * (1.f / kSplitScale) : (1.f / kSplitScale);
-  const float bi = (p.scale && c_ok) ? __ldg(p.bias + c) : 0.f;
+  const int rsub = lane >> 3, cq = lane & 7;
+  const int c = cbase + cq * 4;            // this lane's 4 columns c .. c+3 (N, act_split, ldp are multiples of 4)
+  const bool c_ok = c < p.N;
+  float4 sc = make_float4(1.f / kSplitScale, 1.f / kSplitScale, 1.f / kSplitScale, 1.f / kSplitScale);
+  float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.scale && c_ok) {
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+    sc = make_float4(s4.x * (1.f / kSplitScale), s4.y * (1.f / kSplitScale), s4.z * (1.f / kSplitScale), s4.w * (1.f / kSplitScale));
+    bi = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+  }
   const int act = c >= p.act_split ? p.act1 : p.act0;
   const bool is_relu = act == ACT_RELU, is_leaky = act == ACT_LEAKY;
   const bool plane_col = (OUT & OUT_PLANES) && c < p.ldp;
@@ -236,58 +247,103 @@ __device__ __forceinline__ void store_rows(const KParams& p, const float* tb, in
   __half* const ohi = p.out_hi;
   __half* const olo = p.out_lo;
   const long long n64 = p.N, ld64 = p.ldp;
-  float v[32];
+  float4 v[8];
 #pragma unroll
-  for (int rr = 0; rr < 32; ++rr) v[rr] = tb[rr * 33 + lane];
+  for (int it = 0; it < 8; ++it) v[it] = *reinterpret_cast<const float4*>(tb + (it * 4 + rsub) * TBP + cq * 4);
   if (has_res) {
-    float res[32];
+    float4 res[8];
 #pragma unroll
-    for (int rr = 0; rr < 32; ++rr) {
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + rsub;
       const long long grow = g0 + (rr >> 4) * rowjump + (rr & 15);
-      res[rr] = (c_ok && ((valid >> rr) & 1u)) ? __ldg(p.residual + grow * n64 + c) : 0.f;
+      res[it] = (c_ok && ((valid >> rr) & 1u)) ? __ldg(reinterpret_cast<const float4*>(p.residual + grow * n64 + c))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int rr = 0; rr < 32; ++rr) v[rr] = fmaf(v[rr], sc, bi) + res[rr];
+    for (int it = 0; it < 8; ++it) {
+      v[it].x = fmaf(v[it].x, sc.x, bi.x) + res[it].x;
+      v[it].y = fmaf(v[it].y, sc.y, bi.y) + res[it].y;
+      v[it].z = fmaf(v[it].z, sc.z, bi.z) + res[it].z;
+      v[it].w = fmaf(v[it].w, sc.w, bi.w) + res[it].w;
+    }
   } else {
 #pragma unroll
-    for (int rr = 0; rr < 32; ++rr) v[rr] = fmaf(v[rr], sc, bi);
-  }
-#pragma unroll
-  for (int rr = 0; rr < 32; ++rr) {
-    float x = v[rr];
-    if (kSlowAct) {
-      if (act == ACT_ELU1) x = x > 0.f ? x + 1.f : expf(x);
-      else if (act == ACT_DIVS) x = __fdiv_rn(x, div);
-      else if (is_relu) x = fmaxf(x, 0.f);
-      else if (is_leaky) x = fmaxf(x, 0.01f * x);
-      if (!((rmask_bits >> rr) & 1u)) x = 0.f;
-    } else {
-      const float r = fmaxf(x, 0.f), l = fmaxf(x, 0.01f * x);
-      x = is_relu ? r : (is_leaky ? l : x);
+    for (int it = 0; it < 8; ++it) {
+      v[it].x = fmaf(v[it].x, sc.x, bi.x);
+      v[it].y = fmaf(v[it].y, sc.y, bi.y);
+      v[it].z = fmaf(v[it].z, sc.z, bi.z);
+      v[it].w = fmaf(v[it].w, sc.w, bi.w);
     }
-    v[rr] = x;
   }
 #pragma unroll
-  for (int rr = 0; rr < 32; ++rr) {
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rsub;
+    float x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (kSlowAct) {
+        if (act == ACT_ELU1) {  // elu(x) + 1, straight-line (exp on the clamped argument, then select)
+          const float ex = expf(fminf(x[e], 0.f));
+          x[e] = x[e] > 0.f ? x[e] + 1.f : ex;
+        } else if (act == ACT_DIVS) x[e] = __fdiv_rn(x[e], div);
+        else if (is_relu) x[e] = fmaxf(x[e], 0.f);
+        else if (is_leaky) x[e] = fmaxf(x[e], 0.01f * x[e]);
+        if (!((rmask_bits >> rr) & 1u)) x[e] = 0.f;
+      } else {
+        const float r = fmaxf(x[e], 0.f), l = fmaxf(x[e], 0.01f * x[e]);
+        x[e] = is_relu ? r : (is_leaky ? l : x[e]);
+      }
+      if (!c_ok) x[e] = 0.f;  // pad channels of the fp16 planes are zero
+    }
     const bool ok = (valid >> rr) & 1u;
     const long long grow = g0 + (rr >> 4) * rowjump + (rr & 15);
-    if ((OUT & OUT_F32) && ok && c_ok) of[grow * n64 + c] = v[rr];
+    if ((OUT & OUT_F32) && ok && c_ok) *reinterpret_cast<float4*>(of + grow * n64 + c) = make_float4(x[0], x[1], x[2], x[3]);
     if (OUT & OUT_PLANES) {
-      const float x = c_ok ? v[rr] : 0.f;  // pad channels of the fp16 planes are zero
-      const __half h = __float2half_rn(x);
-      const __half l = __float2half_rn((x - __half2float(h)) * kSplitScale);
+      const __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn((x[0] - f01.x) * kSplitScale, (x[1] - f01.y) * kSplitScale);
+      const __half2 l23 = __floats2half2_rn((x[2] - f23.x) * kSplitScale, (x[3] - f23.y) * kSplitScale);
       if (ok && plane_col) {
-        ohi[grow * ld64 + c] = h;
-        olo[grow * ld64 + c] = l;
+        uint2 uh, ul;
+        uh.x = *reinterpret_cast<const unsigned int*>(&h01); uh.y = *reinterpret_cast<const unsigned int*>(&h23);
+        ul.x = *reinterpret_cast<const unsigned int*>(&l01); ul.y = *reinterpret_cast<const unsigned int*>(&l23);
+        *reinterpret_cast<uint2*>(ohi + grow * ld64 + c) = uh;
+        *reinterpret_cast<uint2*>(olo + grow * ld64 + c) = ul;
       }
+    }
+  }
+}
+
+// L2 prefetch of the residual block a warp will consume in a LATER tile: lane = row, one 128-byte line per owned
+// 32-column group.
+__device__ __forceinline__ void prefetch_residual(const KParams& p, const TileCoord& tc, int lane, int q, int half) {
+  long long g0, rowjump;
+  bool ok;
+  if (p.mode == 0) {
+    g0 = (long long)tc.m_tile * BM + q * 32;
+    rowjump = 16;
+    ok = g0 + lane < p.M;
+  } else {
+    const int oh = tc.oh0 + q * 2, ow = tc.ow0;
+    g0 = ((long long)tc.img * p.OH + oh) * p.OW + ow;
+    rowjump = p.OW;
+    ok = (oh + (lane >> 4) < p.OH) && (ow + (lane & 15) < p.OW);
+  }
+  if (!ok) return;
+  const long long grow = g0 + (lane >> 4) * rowjump + (lane & 15);
+  const int n0 = tc.n_tile * p.bn;
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) {
+    const int c0 = (gi * 2 + half) * 32;
+    if (c0 < p.bn && n0 + c0 < p.N) {
+      const float* ptr = p.residual + grow * (long long)p.N + n0 + c0;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
     }
   }
 }
 
 template <int OUT, bool kSlowAct>
 __device__ __forceinline__ void store_group(const KParams& p, const float* tb, int lane, int q, const TileCoord& tc, int cbase) {
-  const int c = cbase + lane;
-  const bool c_ok = c < p.N;
   long long g0, rowjump;
   bool my_ok;  // validity of row rr == lane
   if (p.mode == 0) {
@@ -306,62 +362,66 @@ __device__ __forceinline__ void store_group(const KParams& p, const float* tb, i
     const long long grow = g0 + (lane >> 4) * rowjump + (lane & 15);
     rmask_bits = __ballot_sync(0xffffffffu, my_ok && p.row_mask[grow] != 0);
   }
-  store_rows<OUT, kSlowAct>(p, tb, lane, c, c_ok, g0, rowjump, valid, rmask_bits);
+  store_rows<OUT, kSlowAct>(p, tb, lane, cbase, g0, rowjump, valid, rmask_bits);
 }
 
 // Copy one of the four register-resident 32-column accumulator groups into the warp's smem tile.  The group loop in
 // the epilogues is deliberately NOT unrolled (one copy of the per-group code keeps the SASS small enough for the
 // instruction cache); the switch gives every case static register indices.
 __device__ __forceinline__ void stage_group(float* tb, int lane, const float (&acc)[4][32], int gi) {
+  float4* dst = reinterpret_cast<float4*>(tb + lane * TBP);
+#define GIMB_STAGE(G)                                                                                   \
+  _Pragma("unroll") for (int j4 = 0; j4 < 8; ++j4)                                                      \
+      dst[j4] = make_float4(acc[G][j4 * 4], acc[G][j4 * 4 + 1], acc[G][j4 * 4 + 2], acc[G][j4 * 4 + 3]);
   switch (gi) {
-    case 0:
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[0][j];
-      break;
-    case 1:
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[1][j];
-      break;
-    case 2:
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[2][j];
-      break;
-    default:
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[3][j];
-      break;
+    case 0: GIMB_STAGE(0) break;
+    case 1: GIMB_STAGE(1) break;
+    case 2: GIMB_STAGE(2) break;
+    default: GIMB_STAGE(3) break;
   }
+#undef GIMB_STAGE
 }
 
 // ---- per-group (32 rows x 32 columns per warp) bodies of the coarse-matching epilogues.  `tb` is the warp's
 // padded smem tile holding the raw accumulators row-per-lane: tb[lane * 33 + j] = 2^8 * <f0[row], f1[col j]>.
 __device__ __forceinline__ void corr_stats_group(const KParams& p, float* tb, int lane, int q, int img, int m_tile, int cbase,
-                                              bool row_ok, bool rmasked, float& rm, float& rs) {
-  float* mine = tb + lane * 33;
-  // sim = dot / C / T (same formula as the fp32 sweeps), masked_fill(-1e9), invalid -> -inf; group row max
+                                                 bool row_ok, bool rmasked, float& rm, float& rs) {
+  // straight-line, register resident: v[j] = sim(row, cbase + j)
+  float v[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 t4 = *reinterpret_cast<const float4*>(tb + lane * TBP + j4 * 4);
+    v[j4 * 4] = t4.x * p.sim_scale; v[j4 * 4 + 1] = t4.y * p.sim_scale;
+    v[j4 * 4 + 2] = t4.z * p.sim_scale; v[j4 * 4 + 3] = t4.w * p.sim_scale;
+  }
+  if (p.mask1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = cbase + j;
+      if (rmasked || (c < p.S && p.mask1[(long long)img * p.S + c] == 0)) v[j] = -1e9f;
+    }
+  } else if (rmasked) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = -1e9f;
+  }
   float gm = -INFINITY;
-#pragma unroll 4
+#pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const int c = cbase + j;
-    float x = __fdiv_rn(mine[j] * (1.f / kSplitScale) * p.inv_c, p.temperature);
-    const bool cmasked = p.mask1 && c < p.S && p.mask1[(long long)img * p.S + c] == 0;
-    if (rmasked || cmasked) x = -1e9f;
-    if (c >= p.S || !row_ok) x = -INFINITY;
-    mine[j] = x;
-    gm = fmaxf(gm, x);
+    if (cbase + j >= p.S || !row_ok) v[j] = -INFINITY;
+    gm = fmaxf(gm, v[j]);
   }
   // row partial (softmax over dim 2): online (max, sum exp) over this thread's columns
   if (gm > rm) { rs *= __expf(rm - gm); rm = gm; }
   if (rm > -INFINITY) {
-    float a = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) a += __expf(mine[j] - rm);
-    rs += a;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) { a0 += __expf(v[j] - rm); a1 += __expf(v[j + 1] - rm); }
+    rs += a0 + a1;
   }
   // column partial (softmax over dim 1) over the 32 rows of this warp
-  float v[32], w[32];
+  float w[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { v[j] = mine[j]; w[j] = v[j]; }
+  for (int j = 0; j < 32; ++j) w[j] = v[j];
   const float cm = transpose_reduce(w, lane, OpMax());
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
@@ -374,27 +434,43 @@ __device__ __forceinline__ void corr_stats_group(const KParams& p, float* tb, in
 }
 
 __device__ __forceinline__ void corr_conf_group(const KParams& p, const float* tb, int lane, int img, int cbase, long long row,
-                                             bool rmasked, unsigned long long& best) {
-  const float* mine = tb + lane * 33;
+                                                bool rmasked, unsigned long long& best) {
   const float2 rst = p.rowstat[row];
-#pragma unroll 2
+  const long long gc0 = (long long)img * p.S + cbase;
+  const int ncol = min(32, p.S - cbase);
+  // conf = softmax_col * softmax_row <= exp((x - rmax) + (x - cmax)): only entries that can exceed the threshold are
+  // evaluated exactly; all others can never be a match (coarse_matching.py:174-190).  Pass 1 builds the candidate
+  // bit mask branch-free; the (rare) candidates are then evaluated with the reference's formula.
+  unsigned cand = 0u;
+  float xs[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 t4 = *reinterpret_cast<const float4*>(tb + lane * TBP + j4 * 4);
+    xs[j4 * 4] = t4.x; xs[j4 * 4 + 1] = t4.y; xs[j4 * 4 + 2] = t4.z; xs[j4 * 4 + 3] = t4.w;
+  }
+#pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const int c = cbase + j;
-    if (c >= p.S) break;
-    const long long gc = (long long)img * p.S + c;
-    float x = __fdiv_rn(mine[j] * (1.f / kSplitScale) * p.inv_c, p.temperature);
-    if (rmasked || (p.mask1 && p.mask1[gc] == 0)) x = -1e9f;
-    const float2 cst = __ldg(&p.colstat[gc]);
-    // conf = softmax_col * softmax_row <= exp((x - rmax) + (x - cmax)): only entries that can exceed the threshold
-    // are evaluated exactly; all others can never be a match (coarse_matching.py:174-190)
-    const float t = (x - rst.x) + (x - cst.x);
-    if (t > p.thr_log) {
-      const float conf = __fdiv_rn(expf(x - cst.x), cst.y) * __fdiv_rn(expf(x - rst.x), rst.y);
-      const unsigned int bits = __float_as_uint(conf);
-      const unsigned long long pk = ((unsigned long long)bits << 32) | (unsigned long long)(~(unsigned int)c);
-      best = pk > best ? pk : best;
-      atomicMax(&p.colbest[gc], bits);
+    float x = xs[j] * p.sim_scale;
+    float cmax = INFINITY;
+    if (j < ncol) {
+      cmax = __ldg(&p.colstat[gc0 + j].x);
+      if (rmasked || (p.mask1 && p.mask1[gc0 + j] == 0)) x = -1e9f;
     }
+    const float t = (x - rst.x) + (x - cmax);
+    cand |= (t > p.thr_log) ? (1u << j) : 0u;
+  }
+  while (cand) {
+    const int j = __ffs(cand) - 1;
+    cand &= cand - 1;
+    float x = tb[lane * TBP + j] * p.sim_scale;
+    if (rmasked || (p.mask1 && p.mask1[gc0 + j] == 0)) x = -1e9f;
+    const float2 cst = __ldg(&p.colstat[gc0 + j]);
+    const float conf = __fdiv_rn(expf(x - cst.x), cst.y) * __fdiv_rn(expf(x - rst.x), rst.y);
+    const unsigned int bits = __float_as_uint(conf);
+    const unsigned int c = (unsigned int)(cbase + j);
+    const unsigned long long pk = ((unsigned long long)bits << 32) | (unsigned long long)(~c);
+    best = pk > best ? pk : best;
+    atomicMax(&p.colbest[gc0 + j], bits);
   }
 }
 
@@ -406,7 +482,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   uint8_t* gen = smem_raw + (base - raw);
   const uint32_t bars = base + p.stages * p.stage_bytes;        // barrier block
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + p.stages * p.stage_bytes + 256);
-  float* tbuf = reinterpret_cast<float*>(gen + p.stages * p.stage_bytes + 512);  // [NUM_EPI_WARPS][32][33] transpose tiles
+  float* tbuf = reinterpret_cast<float*>(gen + p.stages * p.stage_bytes + 512);  // [NUM_EPI_WARPS][32][TBP] transpose tiles
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
   auto tfull_bar = [&](int b) { return bars + 128u + 8u * b; };
@@ -559,8 +635,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         row_ok = oh < p.OH && ow < p.OW;
         row = ((long long)tc.img * p.OH + oh) * p.OW + ow;
       }
-      float rmask = 1.f;
-      if (EPI == EPI_STORE && p.row_mask && row_ok) rmask = (float)p.row_mask[row];
+      if (EPI == EPI_STORE && (OUT & OUT_RESIDUAL) && p.residual) {
+        if (t == (int)blockIdx.x) prefetch_residual(p, tc, lane, q, half);  // first tile: no lead time available
+        const int tn = t + gridDim.x;
+        if (tn < p.num_tiles) prefetch_residual(p, decode_tile(p, tn), lane, q, half);
+      }
 
       // ---- drain the chunk accumulators into fp32 registers (round-to-nearest adds)
       float acc[4][32];
@@ -593,7 +672,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       // The per-group math lives in __noinline__ functions fed from the warp's smem tile: fully unrolled, the
       // epilogue was ~100 KB of straight-line SASS and ran instruction-fetch bound (ncu: stalled_no_instructions).
       if constexpr (EPI == EPI_CORR_STATS) {
-        float* tb = tbuf + (warp - 4) * (32 * 33);
+        float* tb = tbuf + (warp - 4) * (32 * TBP);
         const bool rmasked = p.mask0 && row_ok && p.mask0[row] == 0;
         float rm = -INFINITY, rs = 0.f;
 #pragma unroll 1
@@ -608,7 +687,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         continue;
       }
       if constexpr (EPI == EPI_CORR_CONF) {
-        float* tb = tbuf + (warp - 4) * (32 * 33);
+        float* tb = tbuf + (warp - 4) * (32 * TBP);
         const bool rmasked = p.mask0 && row_ok && p.mask0[row] == 0;
         unsigned long long best = 0ull;
 #pragma unroll 1
@@ -627,7 +706,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       // column-per-lane.  Each warp transposes its 32 x 32 block through a private padded smem tile, so every
       // global access in store_group() is one contiguous 128-byte (fp32) or 64-byte (fp16) segment per warp
       // instruction.  (Row-per-lane stores cost 32 LSU wavefronts per instruction.)
-      float* tb = tbuf + (warp - 4) * (32 * 33);
+      float* tb = tbuf + (warp - 4) * (32 * TBP);
 #pragma unroll 1
       for (int gi = 0; gi < 4; ++gi) {
         const int c0 = (gi * 2 + half) * 32;
@@ -886,6 +965,9 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   p.inv_c = 1.f / (float)c.C;
   p.temperature = c.temperature;
   p.thr_log = c.thr > 0.f ? logf(c.thr) - 1e-3f : -INFINITY;
+  // sim = <f0, f1> / C / T; the accumulator carries 2^8 * <f0, f1>.  One multiply by the fp32-rounded constant
+  // (differs from the reference's `/ T` by at most 1 ulp of sim, far below the fp32 noise of the dot product).
+  p.sim_scale = (float)(1.0 / ((double)kSplitScale * (double)c.C * (double)c.temperature));
   p.rowpart = c.rowpart; p.colpart = c.colpart;
   umma_corr_parts(c.L, c.S, &p.row_parts, &p.col_parts);
   p.rowstat = c.rowstat; p.colstat = c.colstat; p.rowbest = c.rowbest; p.colbest = c.colbest;

@@ -72,19 +72,20 @@ def run_layer(B, H, W, C1, Cout, k, stride, C2=0, bn=False, residual=False, act=
 
 SHAPES = [
     # B, H, W, C1, Cout, k, stride, kwargs
-    (1, 300, 1, 256, 256, 1, 1, {}),                                        # Linear with an M tail
+    (1, 300, 1, 256, 256, 1, 1, dict(planes=False)),                        # Linear with an M tail (fp32 out)
+    (1, 300, 1, 256, 256, 1, 1, dict(residual=True)),                       # fp32 + planes + residual variant
     (1, 64, 64, 64, 64, 1, 1, dict(bn=True, act="relu")),                   # l1 conv1, N = 64
     (1, 4800, 1, 256, 512, 1, 1, dict(C2=256, act="relu")),                 # mlp.0 on cat[x, msg], two N tiles
     (2, 24, 40, 64, 64, 3, 1, dict(bn=True, act="relu")),                   # l1 conv2
     (1, 16, 32, 196, 196, 3, 1, dict(bn=True, act="leaky")),                # FPN 196-channel 3x3 (pitch 200, bn 208)
-    (1, 16, 32, 196, 128, 3, 1, {}),                                        # layer1_outconv2.3
+    (1, 16, 32, 196, 128, 3, 1, dict(planes=False)),                        # layer1_outconv2.3 (fp32 out)
     (2, 32, 48, 128, 128, 3, 2, dict(bn=True, act="relu")),                 # stride-2 3x3 (phase views)
     (2, 32, 48, 256, 512, 1, 2, dict(bn=True)),                             # stride-2 1x1 downsample
     (1, 60, 80, 256, 1024, 1, 1, dict(bn=True, residual=True, act="relu")), # l3 conv3 + identity, 60 rows (tile tail)
     (1, 60, 80, 1024, 256, 1, 1, dict(bn=True, act="relu")),                # K = 1024
     (1, 60, 80, 256, 256, 3, 1, dict(bn=True, act="relu")),                 # K = 2304
-    (1, 1000, 1, 256, 512, 1, 1, dict(act="elu1", act1="divs", split=256, div=4800.0, mask=True)),  # kv projection
-    (1, 777, 1, 128, 128, 1, 1, dict(act="elu1", mask=True)),               # fine q projection
+    (1, 1000, 1, 256, 512, 1, 1, dict(act="elu1", act1="divs", split=256, div=4800.0, mask=True, planes=False)),  # kv projection (fp32 out)
+    (1, 777, 1, 128, 128, 1, 1, dict(act="elu1", mask=True, planes=False)),  # fine q projection (fp32 out)
 ]
 
 
