@@ -210,6 +210,7 @@ struct Epi {
   const float* scale = nullptr;
   const float* bias = nullptr;
   const float* residual = nullptr;
+  const SplitPlanes* residual_planes = nullptr;  // tcgen05 engine: identity carried as fp16 planes
   const uint8_t* row_mask = nullptr;
   int act0 = ACT_NONE, act1 = ACT_NONE, act_split = 1 << 30;
   float div = 1.f;
@@ -240,15 +241,16 @@ int gemm(Fwd& F, const Wt& wt, int cin1, int cin2, int cout, int k, int stride, 
     g.OH = OH; g.OW = OW; g.ldk = wt.ldk;
   }
   g.scale = e.scale; g.bias = e.bias; g.residual = e.residual; g.row_mask = e.row_mask;
+  if (e.residual_planes) g.residual_planes = *e.residual_planes;
   g.act0 = e.act0; g.act1 = e.act1; g.act_split = e.act_split; g.div = e.div;
   g.out_f32 = out.f32; g.out = out.sp;
   return umma_gemm(F.ctx, g);
 }
 
 int run_conv(Fwd& F, const Conv& c, const ActT& in, int B, int H, int W, int stride, int act, const float* residual,
-             const ActT& out) {
+             const ActT& out, const SplitPlanes* residual_planes = nullptr) {
   Epi e;
-  e.scale = c.s; e.bias = c.b; e.residual = residual; e.act0 = e.act1 = act;
+  e.scale = c.s; e.bias = c.b; e.residual = residual; e.residual_planes = residual_planes; e.act0 = e.act1 = act;
   return gemm(F, c.wt, c.cin, 0, c.cout, c.k, stride, in, nullptr, B, H, W, e, out);
 }
 
@@ -260,8 +262,9 @@ int backbone(Fwd& F, const float* color, int B, int H, int W, float* feat_c, flo
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
   const size_t P2 = (size_t)B * H2 * W2, P4 = (size_t)B * H4 * W4, P8 = (size_t)B * H8 * W8;
   size_t mark = A.mark();
-  // block outputs: fp32 (identity path) + split planes (next GEMM operand)
-  ActT xs[3] = {F.alloc(P2, 256, true, true), F.alloc(P4, 512, true, true), F.alloc(P8, 1024, true, true)};
+  // block outputs.  tcgen05 engine: fp16 planes only - they are the next GEMM operand AND the identity of the
+  // next block (x = hi + lo * 2^-8); the fp32 copy would add 8 B/element of HBM traffic to every block.
+  ActT xs[3] = {F.alloc(P2, 256, false, true), F.alloc(P4, 512, false, true), F.alloc(P8, 1024, false, true)};
   {
     size_t mk = A.mark();
     ActT x0 = F.alloc(P2, 64, false, true);
@@ -280,13 +283,9 @@ int backbone(Fwd& F, const float* color, int B, int H, int W, float* feat_c, flo
         GIMB_CHECK(ctx.dry || !A.overflow, "backbone: workspace exhausted");
         GIMB_TRY(run_conv(F, b.c1, cur, B, cH, cW, 1, ACT_RELU, nullptr, u1));
         GIMB_TRY(run_conv(F, b.c2, u1, B, cH, cW, b.stride, ACT_RELU, nullptr, u2));
-        if (b.has_ds) {
-          ActT idn;  // the projected identity is only ever read as fp32 residual
-          idn.f32 = xo.f32; idn.C = xo.C;
-          GIMB_TRY(run_conv(F, b.ds, cur, B, cH, cW, b.stride, ACT_NONE, nullptr, idn));
-        }
-        // identity (xo.f32) is read and overwritten element-wise by the same thread: in-place is safe
-        GIMB_TRY(run_conv(F, b.c3, u2, B, oH, oW, 1, ACT_RELU, xo.f32, xo));
+        if (b.has_ds) GIMB_TRY(run_conv(F, b.ds, cur, B, cH, cW, b.stride, ACT_NONE, nullptr, xo));
+        // the identity (xo) is read and overwritten element-wise by the same thread: in-place is safe
+        GIMB_TRY(run_conv(F, b.c3, u2, B, oH, oW, 1, ACT_RELU, F.tc() ? nullptr : xo.f32, xo, xo.planes()));
         A.release(mk2);
         cur = xo; cH = oH; cW = oW;
       }

@@ -68,6 +68,9 @@ struct KParams {
   __half* out_lo;
   __half* out_h8;
   int ldp;
+  const __half* res_hi;  // residual as split planes (OUT_RES_PLANES), pitch ldr
+  const __half* res_lo;
+  int ldr;
   // ---- coarse-matching sweeps (EPI_CORR_*): batch of nb problems, A = f0[b] [L,C], B = f1[b] [S,C]
   int nb, L, S, tiles_per_batch;
   const uint8_t* mask0;
@@ -219,7 +222,7 @@ struct OpAdd { __device__ __forceinline__ float operator()(float a, float b) con
 // Row rr of the warp maps to global row g0 + (rr >> 4) * rowjump + (rr & 15) (mode 0: rowjump = 16, i.e. g0 + rr;
 // mode 1: two 16-pixel runs of the 8 x 16 patch, rowjump = OW).  Everything row-invariant is hoisted; the residual
 // block is prefetched into registers (32 independent coalesced loads in flight) before it is consumed.
-enum { OUT_F32 = 1, OUT_PLANES = 2, OUT_RESIDUAL = 4 };
+enum { OUT_F32 = 1, OUT_PLANES = 2, OUT_RESIDUAL = 4, OUT_RES_PLANES = 8 };  // RES_PLANES: residual given as fp16 planes
 
 // Vectorised walk over the warp's 32 x 32 block: lane = (row_sub = lane / 8, column quad = lane % 8); one
 // iteration covers 4 rows x 32 columns with 128-bit accesses (4 contiguous 128-byte row segments per warp
@@ -242,6 +245,7 @@ __device__ __forceinline__ void store_rows(const KParams& p, const float* tb, in
   const bool is_relu = act == ACT_RELU, is_leaky = act == ACT_LEAKY;
   const bool plane_col = (OUT & OUT_PLANES) && c < p.ldp;
   const bool has_res = (OUT & OUT_RESIDUAL) && p.residual != nullptr;
+  const bool has_resp = (OUT & OUT_RES_PLANES) != 0;
   const float div = p.div;
   float* const of = p.out_f32;
   __half* const ohi = p.out_hi;
@@ -265,6 +269,29 @@ __device__ __forceinline__ void store_rows(const KParams& p, const float* tb, in
       v[it].y = fmaf(v[it].y, sc.y, bi.y) + res[it].y;
       v[it].z = fmaf(v[it].z, sc.z, bi.z) + res[it].z;
       v[it].w = fmaf(v[it].w, sc.w, bi.w) + res[it].w;
+    }
+  } else if (has_resp) {
+    // identity carried as fp16 planes: x = hi + lo * 2^-8 (exact to 2^-22 relative)
+    uint2 rh[8], rl[8];
+    const long long lr64 = p.ldr;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + rsub;
+      const long long grow = g0 + (rr >> 4) * rowjump + (rr & 15);
+      const bool ld = c_ok && ((valid >> rr) & 1u);
+      rh[it] = ld ? *reinterpret_cast<const uint2*>(p.res_hi + grow * lr64 + c) : make_uint2(0u, 0u);
+      rl[it] = ld ? *reinterpret_cast<const uint2*>(p.res_lo + grow * lr64 + c) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&rh[it].x));
+      const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&rh[it].y));
+      const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&rl[it].x));
+      const float2 l23 = __half22float2(*reinterpret_cast<const __half2*>(&rl[it].y));
+      v[it].x = fmaf(v[it].x, sc.x, bi.x) + fmaf(l01.x, 1.f / kSplitScale, h01.x);
+      v[it].y = fmaf(v[it].y, sc.y, bi.y) + fmaf(l01.y, 1.f / kSplitScale, h01.y);
+      v[it].z = fmaf(v[it].z, sc.z, bi.z) + fmaf(l23.x, 1.f / kSplitScale, h23.x);
+      v[it].w = fmaf(v[it].w, sc.w, bi.w) + fmaf(l23.y, 1.f / kSplitScale, h23.y);
     }
   } else {
 #pragma unroll
@@ -893,11 +920,15 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   p.scale = g.scale; p.bias = g.bias; p.residual = g.residual; p.row_mask = g.row_mask;
   p.act0 = g.act0; p.act1 = g.act1; p.act_split = g.act_split; p.div = g.div;
   p.out_f32 = g.out_f32; p.out_hi = g.out.hi; p.out_lo = g.out.lo; p.out_h8 = g.out.h8; p.ldp = g.out.ld;
+  p.res_hi = g.residual_planes.hi; p.res_lo = g.residual_planes.lo; p.ldr = g.residual_planes.ld;
 
   p.nb = 1;
   const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
   const bool slow = g.act0 >= ACT_ELU1 || g.act1 >= ACT_ELU1 || g.row_mask != nullptr;
   const bool f32 = g.out_f32 != nullptr, planes = g.out.hi != nullptr, res = g.residual != nullptr;
+  const bool resp = g.residual_planes.hi != nullptr;
+  GIMB_CHECK(!(res && resp), "umma_gemm: residual given twice");
+  if (resp) GIMB_CHECK(g.residual_planes.lo && g.residual_planes.ld % 8 == 0 && g.residual_planes.ld >= g.N, "umma_gemm: bad residual planes");
   GIMB_CHECK(g.out.h8 == nullptr, "umma_gemm: the GEMM epilogue does not produce the h8 plane");
   const int grid = std::min(p.num_tiles, ctx.sm_count);
   cudaError_t aerr = cudaSuccess;
@@ -911,7 +942,13 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     }                                                                                                             \
     umma_gemm_kernel<EPI_STORE, OUTV, SLOWV><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);                   \
   } while (0)
-  if (f32 && !planes && !res && slow) GIMB_LAUNCH_VARIANT(OUT_F32, true);
+  if (resp) {
+    if (!f32 && planes && !slow) GIMB_LAUNCH_VARIANT(OUT_PLANES | OUT_RES_PLANES, false);
+    else {
+      set_error("umma_gemm: residual planes are supported for plane-only output");
+      return 1;
+    }
+  } else if (f32 && !planes && !res && slow) GIMB_LAUNCH_VARIANT(OUT_F32, true);
   else if (f32 && !planes && !res) GIMB_LAUNCH_VARIANT(OUT_F32, false);
   else if (!f32 && planes && !res && !slow) GIMB_LAUNCH_VARIANT(OUT_PLANES, false);
   else if (f32 && planes && !slow) GIMB_LAUNCH_VARIANT(OUT_F32 | OUT_PLANES | OUT_RESIDUAL, false);

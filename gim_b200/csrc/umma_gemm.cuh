@@ -42,6 +42,7 @@ struct UmmaGemm {
   const float* scale = nullptr;
   const float* bias = nullptr;
   const float* residual = nullptr;   // [M, N] fp32, pitch N
+  SplitPlanes residual_planes;       // alternatively the residual as fp16 planes (plane-only output variant)
   const uint8_t* row_mask = nullptr;
   int act0 = ACT_NONE, act1 = ACT_NONE, act_split = 1 << 30;
   float div = 1.f;
