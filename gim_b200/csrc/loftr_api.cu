@@ -43,7 +43,9 @@ struct EncLayer {
 
 constexpr int FINE_CHUNK = 16384;  // matches per fine-stage pass
 
-inline int pitch8(int c) { return (c + 7) / 8 * 8; }
+// channel pitch of fp16 planes: multiples of 32 elements (64 B) so that every TMA box row (32 channels) is one
+// aligned 64-byte segment; only the 196-channel FPN tensors are actually padded (to 224)
+inline int pitch8(int c) { return (c + 31) / 32 * 32; }
 
 }  // namespace
 }  // namespace gimb
@@ -83,19 +85,19 @@ int find(gimb_loftr* m, const std::string& name, const float** out, std::vector<
   return 0;
 }
 
-// carve fp16 planes (h8, lo, hi) for a weight [rows = cout*taps][cin] out of m->dplanes and fill them.
+// carve fp16 planes (hi, lo) for a weight [rows = cout*taps][cin] out of m->dplanes and fill them.
 // With m->dplanes == nullptr only the size is accumulated (first pass).
 int make_weight_planes(gimb_loftr* m, Ctx& ctx, Wt* wt, int cout, int taps, int cin) {
   wt->ldk = pitch8(cin);
   const size_t n = (size_t)cout * taps * wt->ldk;
-  __half* ptr[3];
-  for (int i = 0; i < 3; ++i) {
+  __half* ptr[2];
+  for (int i = 0; i < 2; ++i) {
     m->dplanes_top = (m->dplanes_top + 255) / 256 * 256;
     ptr[i] = m->dplanes ? (__half*)(m->dplanes + m->dplanes_top) : nullptr;
     m->dplanes_top += n * sizeof(__half);
   }
   if (!m->dplanes) return 0;
-  wt->wp.h8 = ptr[0]; wt->wp.lo = ptr[1]; wt->wp.hi = ptr[2];
+  wt->wp.hi = ptr[0]; wt->wp.lo = ptr[1];
   SplitPlanes tap_view = wt->wp;
   tap_view.ld = wt->ldk;  // rows of cin values, pitch ldk
   GIMB_TRY(split_planes(ctx, wt->w, (int64_t)cout * taps, cin, cin, tap_view));
@@ -443,7 +445,7 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
   ctx.marker = &prof;
 
   // persistent buffers (bottom of the stack): coarse tokens (both images back to back) and the fine maps
-  ActT tok = F.alloc((size_t)n * (L + S), C, true, true, true);
+  ActT tok = F.alloc((size_t)n * (L + S), C, true, true);
   float* fc0 = tok.f32;
   float* fc1 = tok.f32 + (size_t)n * L * C;
   float* ff = A.alloc<float>((size_t)n * ((size_t)h0f * w0f + (size_t)h1f * w1f) * CF);

@@ -63,7 +63,7 @@ extern "C" int gimb_test_conv(const float* in, const float* in2, int B, int H, i
   const int taps = ksize * ksize;
   const int ldk = pitch8(Cin);
   b.ld = taps * ldk;
-  b.hi = A.alloc<__half>((size_t)Cout * b.ld); b.lo = A.alloc<__half>((size_t)Cout * b.ld); b.h8 = A.alloc<__half>((size_t)Cout * b.ld);
+  b.hi = A.alloc<__half>((size_t)Cout * b.ld); b.lo = A.alloc<__half>((size_t)Cout * b.ld);
   {
     SplitPlanes bt = b;
     bt.ld = ldk;  // treat [Cout*taps] rows of Cin -> pitch ldk
@@ -123,7 +123,6 @@ extern "C" int gimb_bench_layer(int B, int H, int W, int C1, int C2, int Cout, i
   const int taps = ksize * ksize, ldk = pitch8(Cin);
   b.ld = taps * ldk;
   b.hi = (__half*)dalloc((size_t)Cout * b.ld * 2, 0x1c); b.lo = (__half*)dalloc((size_t)Cout * b.ld * 2, 0);
-  b.h8 = (__half*)dalloc((size_t)Cout * b.ld * 2, 0x1c);
   float* scale = (flags & 1) ? (float*)dalloc(Cout * 4, 0) : nullptr;
   float* bias = (flags & 1) ? (float*)dalloc(Cout * 4, 0) : nullptr;
   float* res = (flags & 2) ? (float*)dalloc(M * Cout * 4, 0) : nullptr;

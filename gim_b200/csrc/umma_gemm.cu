@@ -4,7 +4,8 @@
 //   warp 0      TMA producer  : cp.async.bulk.tensor (2-D/3-D row tiles or 4-D NHWC patches, OOB zero fill = conv padding)
 //                               into a ring of SWIZZLE_64B shared-memory stages, mbarrier complete_tx
 //   warp 1      MMA issuer    : one elected lane issues 3 x tcgen05.mma.kind::f16 (M=128, N<=256, K=16) per k16 step
-//                               [A_hi*B_h8 + A_hi*B_lo + A_lo*B_hi] into a double-buffered fp32 TMEM accumulator,
+//                               [cross terms A_hi*B_lo + A_lo*B_hi, then A_hi*B_hi with scale-input-d 2^-8] into a
+//                               double-buffered fp32 TMEM accumulator,
 //                               tcgen05.commit frees smem stages / publishes the accumulator
 //   warps 4..11 epilogue      : the tensor core accumulates only CHUNK_KB k-blocks at a time; the chunks are summed
 //                               in fp32 registers with round-to-nearest (tcgen05.ld, 32 lanes x 32 columns).  The MMA
@@ -43,7 +44,7 @@ constexpr int ACC_COLS = 256;
 struct TMaps {
   CUtensorMap a_hi[4], a_lo[4];  // mode 1 stride 2: four phase views; otherwise index 0
   CUtensorMap a2_hi, a2_lo;      // mode 0 concat source
-  CUtensorMap b_h8, b_lo, b_hi;
+  CUtensorMap b_lo, b_hi;
 };
 
 struct KParams {
@@ -157,6 +158,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D = A*B + D * 2^-8   (scale-input-d immediate, kind::f16)
+__device__ __forceinline__ void umma_f16_scaled8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 8;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -234,11 +244,10 @@ __device__ __forceinline__ void store_rows(const KParams& p, const float* tb, in
   const int rsub = lane >> 3, cq = lane & 7;
   const int c = cbase + cq * 4;            // this lane's 4 columns c .. c+3 (N, act_split, ldp are multiples of 4)
   const bool c_ok = c < p.N;
-  float4 sc = make_float4(1.f / kSplitScale, 1.f / kSplitScale, 1.f / kSplitScale, 1.f / kSplitScale);
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
   float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.scale && c_ok) {
-    const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + c));
-    sc = make_float4(s4.x * (1.f / kSplitScale), s4.y * (1.f / kSplitScale), s4.z * (1.f / kSplitScale), s4.w * (1.f / kSplitScale));
+    sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
     bi = __ldg(reinterpret_cast<const float4*>(p.bias + c));
   }
   const int act = c >= p.act_split ? p.act1 : p.act0;
@@ -520,7 +529,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi[0]);
     tma_prefetch_desc(&maps.a_lo[0]);
-    tma_prefetch_desc(&maps.b_h8);
     tma_prefetch_desc(&maps.b_lo);
     tma_prefetch_desc(&maps.b_hi);
   }
@@ -591,9 +599,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             tma_load_4d(sA + A_TILE_BYTES, &maps.a_lo[view], fb, cb * BK, tc.ow0 + dw, tc.oh0 + dh, tc.img);
           }
           const int bb = (p.mode == 0) ? tc.img : 0;  // weights: one matrix; coarse matching: f1 of the same pair
-          tma_load_3d(sB, &maps.b_h8, fb, bk, n0, bb);
+          tma_load_3d(sB, &maps.b_hi, fb, bk, n0, bb);
           tma_load_3d(sB + b_plane, &maps.b_lo, fb, bk, n0, bb);
-          tma_load_3d(sB + 2 * b_plane, &maps.b_hi, fb, bk, n0, bb);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -613,26 +620,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           tc_fence_after();
           const uint32_t tacc = tmem_base + buf * ACC_COLS;
           const int kb_end = min(p.num_kb, kb + p.chunk_kb);
+          // pass 1 over the chunk's stages: the two cross terms  D  = sum_k (A_hi*B_lo + A_lo*B_hi)      [lo = 2^8 * residual]
+          // pass 2 over the same stages:    the main term        D  = sum_k A_hi*B_hi + 2^-8 * D         (scale-input-d = 8
+          // on the first MMA of the pass).  The cross sum is accumulated at its own (small) magnitude and scaled exactly.
+          int st = stage;
+          uint32_t ph = phase;
           bool first = true;
-          for (; kb < kb_end; ++kb) {
-            mbar_wait(full_bar(stage), phase);
+          for (int k2 = kb; k2 < kb_end; ++k2) {
+            mbar_wait(full_bar(st), ph);
             tc_fence_after();
-            const uint32_t sA = base + stage * p.stage_bytes;
+            const uint32_t sA = base + st * p.stage_bytes;
             const uint32_t sB = sA + 2 * A_TILE_BYTES;
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
               const uint32_t koff = kk * 32;  // 16 fp16 = 32 bytes inside the 64-byte swizzle row
               const uint64_t a_hi = make_desc_sw64(sA + koff);
               const uint64_t a_lo = make_desc_sw64(sA + A_TILE_BYTES + koff);
-              const uint64_t b_h8 = make_desc_sw64(sB + koff);
+              const uint64_t b_hi = make_desc_sw64(sB + koff);
               const uint64_t b_lo = make_desc_sw64(sB + b_plane + koff);
-              const uint64_t b_hi = make_desc_sw64(sB + 2 * b_plane + koff);
-              umma_f16(tacc, a_hi, b_h8, p.idesc, first ? 0u : 1u);
-              umma_f16(tacc, a_hi, b_lo, p.idesc, 1);
+              umma_f16(tacc, a_hi, b_lo, p.idesc, first ? 0u : 1u);
               umma_f16(tacc, a_lo, b_hi, p.idesc, 1);
               first = false;
             }
-            umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
+            if (++st == p.stages) { st = 0; ph ^= 1; }
+          }
+          first = true;
+          for (; kb < kb_end; ++kb) {
+            const uint32_t sA = base + stage * p.stage_bytes;
+            const uint32_t sB = sA + 2 * A_TILE_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint32_t koff = kk * 32;
+              const uint64_t a_hi = make_desc_sw64(sA + koff);
+              const uint64_t b_hi = make_desc_sw64(sB + koff);
+              if (first) umma_f16_scaled8(tacc, a_hi, b_hi, p.idesc);
+              else umma_f16(tacc, a_hi, b_hi, p.idesc, 1);
+              first = false;
+            }
+            umma_commit(empty_bar(stage));  // smem stage reusable once every MMA of both passes has read it
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
           umma_commit(tfull_bar(buf));      // chunk accumulator complete
@@ -841,7 +866,7 @@ int split_planes(Ctx& ctx, const float* src, int64_t rows, int cols, int src_ld,
 }
 
 int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
-  GIMB_CHECK(g.a.hi && g.a.lo && g.b.hi && g.b.lo && g.b.h8, "umma_gemm: operand planes missing");
+  GIMB_CHECK(g.a.hi && g.a.lo && g.b.hi && g.b.lo, "umma_gemm: operand planes missing");
   GIMB_CHECK(g.N >= 8 && g.N % 4 == 0, "umma_gemm: N must be a multiple of 4");
   GIMB_CHECK(g.a.ld % 8 == 0 && g.b.ld % 8 == 0, "umma_gemm: plane pitches must be multiples of 8");
   GIMB_CHECK(g.stride == 1 || g.stride == 2, "umma_gemm: stride 1 or 2");
@@ -878,7 +903,6 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     p.ldk = 0;
     const uint64_t Kw = (uint64_t)g.K1 + g.K2;
     GIMB_CHECK((uint64_t)g.b.ld >= Kw, "umma_gemm: weight pitch smaller than K");
-    GIMB_TRY(rows_map(&maps.b_h8, g.b.h8, Kw, g.N, g.b.ld, p.bn));
     GIMB_TRY(rows_map(&maps.b_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn));
     GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn));
   } else {
@@ -906,15 +930,17 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     }
     const uint64_t Kw = (uint64_t)g.KH * g.KW * g.ldk;
     GIMB_CHECK((uint64_t)g.b.ld >= Kw, "umma_gemm: weight pitch smaller than K");
-    GIMB_TRY(rows_map(&maps.b_h8, g.b.h8, Kw, g.N, g.b.ld, p.bn));
     GIMB_TRY(rows_map(&maps.b_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn));
     GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn));
   }
-  p.stage_bytes = 2 * A_TILE_BYTES + 3 * p.bn * BK * 2;
+  p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * BK * 2;
   p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - SMEM_EXTRA) / p.stage_bytes);
-  p.stages = std::max(1, std::min(p.stages, std::max(2, p.num_kb)));
+  p.stages = std::max(2, std::min(p.stages, std::max(3, p.num_kb + 1)));
   p.num_tiles = m_tiles * p.n_tiles;
-  p.chunk_kb = chunk_kb_setting();
+  // K <= 128: one in-TMEM chunk (24 accumulation steps keep the truncation bias at the fp32-FFMA level and save a
+  // drain hand-shake per tile); longer K: chunks of CHUNK_KB k-blocks
+  p.chunk_kb = p.num_kb <= 4 ? p.num_kb : chunk_kb_setting();
+  p.chunk_kb = std::max(1, std::min(p.chunk_kb, p.stages - 1));  // a chunk's stages stay resident for both MMA passes
   p.num_chunks = cdiv(p.num_kb, p.chunk_kb);
   p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
   p.scale = g.scale; p.bias = g.bias; p.residual = g.residual; p.row_mask = g.row_mask;
@@ -970,7 +996,7 @@ void umma_corr_parts(int L, int S, int* row_parts, int* col_parts) {
 }
 
 int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
-  GIMB_CHECK(c.f0.hi && c.f0.lo && c.f1.hi && c.f1.lo && c.f1.h8, "umma_corr: operand planes missing");
+  GIMB_CHECK(c.f0.hi && c.f0.lo && c.f1.hi && c.f1.lo, "umma_corr: operand planes missing");
   GIMB_CHECK(c.C % 32 == 0, "umma_corr: C must be a multiple of 32");
   if (ctx.dry || c.N == 0) return 0;
   KParams p = {};
@@ -990,21 +1016,20 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   p.num_tiles = c.N * p.tiles_per_batch;
   GIMB_TRY(rows_map(&maps.a_hi[0], c.f0.hi, c.C, c.L, c.f0.ld, BM, c.N));
   GIMB_TRY(rows_map(&maps.a_lo[0], c.f0.lo, c.C, c.L, c.f0.ld, BM, c.N));
-  GIMB_TRY(rows_map(&maps.b_h8, c.f1.h8, c.C, c.S, c.f1.ld, p.bn, c.N));
   GIMB_TRY(rows_map(&maps.b_lo, c.f1.lo, c.C, c.S, c.f1.ld, p.bn, c.N));
   GIMB_TRY(rows_map(&maps.b_hi, c.f1.hi, c.C, c.S, c.f1.ld, p.bn, c.N));
-  p.stage_bytes = 2 * A_TILE_BYTES + 3 * p.bn * BK * 2;
+  p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * BK * 2;
   p.stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - SMEM_EXTRA) / p.stage_bytes));
-  p.chunk_kb = chunk_kb_setting();
+  p.chunk_kb = std::max(1, std::min(chunk_kb_setting(), p.stages - 1));
   p.num_chunks = cdiv(p.num_kb, p.chunk_kb);
   p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
   p.mask0 = c.mask0; p.mask1 = c.mask1;
   p.inv_c = 1.f / (float)c.C;
   p.temperature = c.temperature;
   p.thr_log = c.thr > 0.f ? logf(c.thr) - 1e-3f : -INFINITY;
-  // sim = <f0, f1> / C / T; the accumulator carries 2^8 * <f0, f1>.  One multiply by the fp32-rounded constant
+  // sim = <f0, f1> / C / T.  One multiply by the fp32-rounded constant
   // (differs from the reference's `/ T` by at most 1 ulp of sim, far below the fp32 noise of the dot product).
-  p.sim_scale = (float)(1.0 / ((double)kSplitScale * (double)c.C * (double)c.temperature));
+  p.sim_scale = (float)(1.0 / ((double)c.C * (double)c.temperature));
   p.rowpart = c.rowpart; p.colpart = c.colpart;
   umma_corr_parts(c.L, c.S, &p.row_parts, &p.col_parts);
   p.rowstat = c.rowstat; p.colstat = c.colstat; p.rowbest = c.rowbest; p.colbest = c.colbest;

@@ -4,10 +4,11 @@
 //
 // Operand format ("split fp16"): every fp32 value x is carried as two fp16 planes
 //   hi = fp16(x),  lo = fp16((x - hi) * 2^8)
-// and the B operand additionally as h8 = 2^8 * hi (exact).  One fp32 TMEM accumulator receives
-//   D' = A_hi * B_h8  +  A_hi * B_lo  +  A_lo * B_hi      (3 x tcgen05.mma kind::f16 per k16 step)
-// so that D = 2^-8 * D' = A*B up to the dropped lo*lo term (2^-22 relative) - the precision class the
-// survey validated against the fp32 reference ("3 MMAs at the f16 rate").
+// One fp32 TMEM accumulator receives, per chunk of k,
+//   D  = sum_k (A_hi * B_lo + A_lo * B_hi)          (2 x tcgen05.mma kind::f16 per k16 step)
+//   D  = sum_k  A_hi * B_hi  +  2^-8 * D            (1 x per k16 step, the first with scale-input-d = 8)
+// so that D = A*B up to the dropped lo*lo term (2^-22 relative) - the precision class the survey validated
+// against the fp32 reference ("3 MMAs at the f16 rate").
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>

@@ -100,6 +100,7 @@ class LoFTR(nn.Module):
         self._pe_sizes = set()
         self._workspace = None
         self._staging = None
+        self._host_out = None
         self.last_h2d_bytes = 0
         self.last_d2h_bytes = 0
         for p in self.parameters():
@@ -283,8 +284,12 @@ class LoFTR(nn.Module):
                                                              ctypes.byref(need)))
                 if self._staging is None or self._staging.numel() < need.value or self._staging.device != dev:
                     self._staging = torch.empty(need.value, dtype=torch.uint8, device=dev)
-                houts = self._alloc_outputs(cap, torch.device("cpu"), pin=True)
-                ho = self._out_struct(cap, houts)
+                # persistent pinned staging for the D2H copies (pinned allocation per call is slow, and slower still
+                # when several ranks allocate concurrently); the caller gets private copies of rows [0, M)
+                if self._host_out is None or self._host_out["b_ids"].shape[0] < cap:
+                    self._host_out = self._alloc_outputs(cap, torch.device("cpu"), pin=True)
+                houts = self._host_out
+                ho = self._out_struct(houts["b_ids"].shape[0], houts)
                 up, down = ctypes.c_uint64(), ctypes.c_uint64()
                 _lib.check(lib.gimb_loftr_forward_host(self._handle, ptr(c0), ptr(c1), ptr(m0), ptr(m1), ptr(s0),
                                                        ptr(s1), n, h0, w0, h1, w1, self._staging.data_ptr(),
@@ -293,7 +298,7 @@ class LoFTR(nn.Module):
                                                        ctypes.byref(up), ctypes.byref(down), stream))
                 M = m_out.value
                 self.last_h2d_bytes, self.last_d2h_bytes = up.value, down.value
-                res = {k: v[:M] for k, v in houts.items()}
+                res = {k: v[:M].clone() for k, v in houts.items()}
 
         data.update({
             "bs": n, "hw0_i": data["image0"].shape[2:], "hw1_i": data["image1"].shape[2:],
