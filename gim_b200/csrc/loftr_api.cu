@@ -216,6 +216,7 @@ struct Epi {
   const uint8_t* row_mask = nullptr;
   int act0 = ACT_NONE, act1 = ACT_NONE, act_split = 1 << 30;
   float div = 1.f;
+  bool layernorm = false;  // tcgen05 engine only: LayerNorm fused into the epilogue (scale/bias = gamma/beta)
 };
 
 // one GEMM-shaped layer on the selected engine.  in2: channel concat (1x1 only).
@@ -245,6 +246,7 @@ int gemm(Fwd& F, const Wt& wt, int cin1, int cin2, int cout, int k, int stride, 
   g.scale = e.scale; g.bias = e.bias; g.residual = e.residual; g.row_mask = e.row_mask;
   if (e.residual_planes) g.residual_planes = *e.residual_planes;
   g.act0 = e.act0; g.act1 = e.act1; g.act_split = e.act_split; g.div = e.div;
+  g.layernorm = e.layernorm;
   g.out_f32 = out.f32; g.out = out.sp;
   return umma_gemm(F.ctx, g);
 }
@@ -340,9 +342,10 @@ int encoder_layer(Fwd& F, const EncLayer& e, const ActT& x, const ActT& src, int
   ActT q = F.alloc(RL, C, true, false);
   ActT kv = F.alloc(RS, 2 * C, true, false);
   ActT msg = F.alloc(RL, C, false, true);       // attention output -> merge GEMM operand
-  ActT mrg = F.alloc(RL, C, true, true);        // merge output (fp32), LayerNorm'd into planes
+  ActT mrg = F.alloc(RL, C, false, true);       // norm1(merge(msg)): planes on the tcgen05 engine, fp32 on the CUDA-core one
   ActT hid = F.alloc(RL, 2 * C, false, true);
-  ActT o2 = F.alloc(RL, C, true, false);
+  ActT o2;
+  if (!F.tc()) o2 = F.alloc(RL, C, true, false);
   GIMB_CHECK(ctx.dry || !A.overflow, "encoder_layer: workspace exhausted");
   GIMB_TRY(linear(F, e.q, x, nullptr, RL, C, 0, C, ACT_ELU1, ACT_ELU1, 1 << 30, 1.f, xmask, q));
   GIMB_TRY(linear(F, e.kv, src, nullptr, RS, C, 0, 2 * C, ACT_ELU1, ACT_DIVS, C, (float)S, smask, kv));
@@ -350,14 +353,24 @@ int encoder_layer(Fwd& F, const EncLayer& e, const ActT& x, const ActT& src, int
     GIMB_TRY(fine_attention(ctx, q.f32, kv.f32, n, L, C, nhead, msg.f32, msg.planes()));
   else
     GIMB_TRY(linear_attention(ctx, q.f32, kv.f32, (int)n, L, S, C, nhead, msg.f32, msg.planes()));
-  {
+  if (F.tc()) {
+    // merge + norm1 and mlp.2 + norm2 + residual: LayerNorm fused into the GEMM epilogue (the full row is one tile)
+    Epi e1;
+    e1.scale = e.n1g; e1.bias = e.n1b; e1.layernorm = true;
+    ActT o1; o1.sp = mrg.sp; o1.C = C;
+    GIMB_TRY(gemm(F, e.merge, C, 0, C, 1, 1, msg, nullptr, 1, (int)RL, 1, e1, o1));
+    GIMB_TRY(linear(F, e.mlp0, x, &mrg, RL, C, C, 2 * C, ACT_RELU, ACT_RELU, 1 << 30, 1.f, nullptr, hid));
+    Epi e2;
+    e2.scale = e.n2g; e2.bias = e.n2b; e2.layernorm = true; e2.residual = x.f32;
+    GIMB_TRY(gemm(F, e.mlp2, 2 * C, 0, C, 1, 1, hid, nullptr, 1, (int)RL, 1, e2, x));
+  } else {
     ActT o; o.f32 = mrg.f32; o.C = C;
     GIMB_TRY(linear(F, e.merge, msg, nullptr, RL, C, 0, C, ACT_NONE, ACT_NONE, 1 << 30, 1.f, nullptr, o));
+    GIMB_TRY(layernorm(ctx, mrg.f32, e.n1g, e.n1b, nullptr, RL, C, mrg.f32, nullptr));
+    GIMB_TRY(linear(F, e.mlp0, x, &mrg, RL, C, C, 2 * C, ACT_RELU, ACT_RELU, 1 << 30, 1.f, nullptr, hid));
+    GIMB_TRY(linear(F, e.mlp2, hid, nullptr, RL, 2 * C, 0, C, ACT_NONE, ACT_NONE, 1 << 30, 1.f, nullptr, o2));
+    GIMB_TRY(layernorm(ctx, o2.f32, e.n2g, e.n2b, x.f32, RL, C, x.f32, nullptr));
   }
-  GIMB_TRY(layernorm(ctx, mrg.f32, e.n1g, e.n1b, nullptr, RL, C, F.tc() ? nullptr : mrg.f32, mrg.planes()));
-  GIMB_TRY(linear(F, e.mlp0, x, &mrg, RL, C, C, 2 * C, ACT_RELU, ACT_RELU, 1 << 30, 1.f, nullptr, hid));
-  GIMB_TRY(linear(F, e.mlp2, hid, nullptr, RL, 2 * C, 0, C, ACT_NONE, ACT_NONE, 1 << 30, 1.f, nullptr, o2));
-  GIMB_TRY(layernorm(ctx, o2.f32, e.n2g, e.n2b, x.f32, RL, C, x.f32, x.planes()));
   A.release(mark);
   return 0;
 }

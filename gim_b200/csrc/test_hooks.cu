@@ -94,7 +94,7 @@ extern "C" int gimb_test_conv(const float* in, const float* in2, int B, int H, i
 
 // Times the tcgen05 GEMM alone on one layer shape (operands pre-split, buffers allocated here, zero data except a
 // constant fill): `iters` back-to-back launches between two CUDA events on `stream`.  flags: 1 = folded BN,
-// 2 = residual, 4 = fp32 output, 8 = fp16-plane output.
+// 2 = fp32 residual, 4 = fp32 output, 8 = fp16-plane output, 16 = residual as fp16 planes.
 extern "C" int gimb_bench_layer(int B, int H, int W, int C1, int C2, int Cout, int ksize, int stride, int flags, int act,
                                 int iters, float* ms_out, void* stream) {
   GIMB_CHECK(ms_out && iters > 0, "gimb_bench_layer: bad argument");
@@ -128,6 +128,8 @@ extern "C" int gimb_bench_layer(int B, int H, int W, int C1, int C2, int Cout, i
   float* res = (flags & 2) ? (float*)dalloc(M * Cout * 4, 0) : nullptr;
   float* of = (flags & 4) ? (float*)dalloc(M * Cout * 4, 0) : nullptr;
   if (flags & 8) { o.ld = pitch8(Cout); o.hi = (__half*)dalloc(M * o.ld * 2, 0); o.lo = (__half*)dalloc(M * o.ld * 2, 0); }
+  SplitPlanes rp;
+  if (flags & 16) { rp.ld = pitch8(Cout); rp.hi = (__half*)dalloc(M * rp.ld * 2, 0x3c); rp.lo = (__half*)dalloc(M * rp.ld * 2, 0); }
   int rc = 0;
   for (void* p : bufs) if (!p) rc = 1;
   if (rc) { for (void* p : bufs) if (p) cudaFree(p); set_error("gimb_bench_layer: out of memory"); return 1; }
@@ -136,6 +138,7 @@ extern "C" int gimb_bench_layer(int B, int H, int W, int C1, int C2, int Cout, i
   if (ksize == 1 && stride == 1) { g.mode = 0; g.M = M; g.K1 = C1; g.K2 = C2; }
   else { g.mode = 1; g.K1 = Cin; g.B = B; g.H = H; g.W = W; g.KH = g.KW = ksize; g.stride = stride; g.pad = pad; g.OH = OH; g.OW = OW; g.ldk = ldk; }
   g.scale = scale; g.bias = bias; g.residual = res; g.act0 = g.act1 = act; g.out_f32 = of; g.out = o;
+  g.residual_planes = rp;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   rc = umma_gemm(ctx, g);  // warm-up

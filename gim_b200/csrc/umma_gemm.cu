@@ -37,7 +37,8 @@ constexpr int REGS_LOW = 40, REGS_HIGH = 232;           // setmaxnreg split: 4*3
 constexpr int CHUNK_KB_DEFAULT = 2;  // k-blocks (of 32) accumulated inside the tensor core before the fp32 (RN) drain
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int TBP = 36;  // pitch (floats) of the per-warp 32 x 32 transpose tile: 16-byte aligned rows, conflict-free float4 access
-constexpr int SMEM_EXTRA = 1024 /*alignment slack*/ + 512 /*barriers*/ + NUM_EPI_WARPS * 32 * TBP * 4 /*transpose tiles*/;
+constexpr int SMEM_EXTRA = 1024 /*alignment slack*/ + 512 /*barriers*/ + NUM_EPI_WARPS * 32 * TBP * 4 /*transpose tiles*/ +
+                           2 * NUM_EPI_WARPS * 32 * 4 /*LayerNorm row statistics*/;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 
@@ -45,6 +46,7 @@ struct TMaps {
   CUtensorMap a_hi[4], a_lo[4];  // mode 1 stride 2: four phase views; otherwise index 0
   CUtensorMap a2_hi, a2_lo;      // mode 0 concat source
   CUtensorMap b_lo, b_hi;
+  CUtensorMap bh_lo, bh_hi;      // cluster mode: half-height boxes (bn / 2 rows) of the B planes
 };
 
 struct KParams {
@@ -57,6 +59,9 @@ struct KParams {
   int N, n_tiles, bn;
   int stages, stage_bytes;
   int num_tiles, num_kb, num_chunks, chunk_kb;
+  int cluster;       // 1, or 2: CTA pairs share every B (weight) tile through TMA multicast
+  int m_tiles_real;  // cluster mode: m tiles that exist (the pair grid may carry one dummy tile)
+  int n_imgs;
   unsigned idesc;
   const float* scale;
   const float* bias;
@@ -100,18 +105,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// A protocol bug would otherwise hang the GPU: after ~2^28 failed polls the kernel traps instead.
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~0.5 ms pass) instead
+// of spinning - the polling producer / MMA warps were taking a quarter of the issue slots of the schedulers they share
+// with epilogue warps.  A protocol bug would otherwise hang the GPU: after ~2^17 timeouts (~1 min) the kernel traps.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   uint32_t spins = 0;
   do {
-    if (++spins > (1u << 28)) __trap();
+    if (++spins > (1u << 17)) __trap();
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(500000u)
         : "memory");
   } while (!done);
 }
@@ -132,6 +139,22 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
           dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], "
+      "[%2], %6;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -167,6 +190,13 @@ __device__ __forceinline__ void umma_f16_scaled8(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
+// commit that arrives on the same barrier offset in every CTA of `mask` (cluster mode: a smem stage is written by both
+// producers of the pair, so both consumers must release it)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -184,6 +214,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------- tile iteration
+// cluster == 1: CTA b walks tiles b, b + grid, ...   cluster == 2: the pair walks "pair tiles" (two consecutive m tiles,
+// same n tile); CTA rank r of the pair owns m tile 2 * m_pair + r.  Both CTAs of a pair run the same number of iterations.
+__device__ __forceinline__ int tile_count(const KParams& p) { return p.cluster == 2 ? p.num_tiles / 2 : p.num_tiles; }
+__device__ __forceinline__ int tile_first(const KParams& p) { return p.cluster == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
+__device__ __forceinline__ int tile_step(const KParams& p) { return p.cluster == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
+__device__ __forceinline__ int tile_linear(const KParams& p, int it, uint32_t rank) {
+  if (p.cluster != 2) return it;
+  const int m_pair = it / p.n_tiles, n_tile = it - m_pair * p.n_tiles;
+  return (m_pair * 2 + (int)rank) * p.n_tiles + n_tile;
+}
 
 // ------------------------------------------------------------------------------------------- tile decode
 struct TileCoord {
@@ -363,7 +405,7 @@ __device__ __forceinline__ void prefetch_residual(const KParams& p, const TileCo
     const int oh = tc.oh0 + q * 2, ow = tc.ow0;
     g0 = ((long long)tc.img * p.OH + oh) * p.OW + ow;
     rowjump = p.OW;
-    ok = (oh + (lane >> 4) < p.OH) && (ow + (lane & 15) < p.OW);
+    ok = (oh + (lane >> 4) < p.OH) && (ow + (lane & 15) < p.OW) && tc.img < p.n_imgs;
   }
   if (!ok) return;
   const long long grow = g0 + (lane >> 4) * rowjump + (lane & 15);
@@ -372,8 +414,15 @@ __device__ __forceinline__ void prefetch_residual(const KParams& p, const TileCo
   for (int gi = 0; gi < 4; ++gi) {
     const int c0 = (gi * 2 + half) * 32;
     if (c0 < p.bn && n0 + c0 < p.N) {
-      const float* ptr = p.residual + grow * (long long)p.N + n0 + c0;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+      if (p.residual) {
+        const float* ptr = p.residual + grow * (long long)p.N + n0 + c0;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+      } else {
+        const __half* ph = p.res_hi + grow * (long long)p.ldr + n0 + c0;
+        const __half* pl = p.res_lo + grow * (long long)p.ldr + n0 + c0;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ph));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
+      }
     }
   }
 }
@@ -390,7 +439,7 @@ __device__ __forceinline__ void store_group(const KParams& p, const float* tb, i
     const int oh = tc.oh0 + q * 2, ow = tc.ow0;
     g0 = ((long long)tc.img * p.OH + oh) * p.OW + ow;
     rowjump = p.OW;
-    my_ok = (oh + (lane >> 4) < p.OH) && (ow + (lane & 15) < p.OW);
+    my_ok = (oh + (lane >> 4) < p.OH) && (ow + (lane & 15) < p.OW) && tc.img < p.n_imgs;
   }
   const unsigned valid = __ballot_sync(0xffffffffu, my_ok);
   unsigned rmask_bits = 0xffffffffu;
@@ -422,7 +471,7 @@ __device__ __forceinline__ void stage_group(float* tb, int lane, const float (&a
 // padded smem tile holding the raw accumulators row-per-lane: tb[lane * 33 + j] = 2^8 * <f0[row], f1[col j]>.
 __device__ __forceinline__ void corr_stats_group(const KParams& p, float* tb, int lane, int q, int img, int m_tile, int cbase,
                                                  bool row_ok, bool rmasked, float& rm, float& rs) {
-  // straight-line, register resident: v[j] = sim(row, cbase + j)
+  // row view (lane = row): v[j] = sim(row, cbase + j), straight-line and register resident
   float v[32];
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
@@ -454,24 +503,32 @@ __device__ __forceinline__ void corr_stats_group(const KParams& p, float* tb, in
     for (int j = 0; j < 32; j += 2) { a0 += __expf(v[j] - rm); a1 += __expf(v[j + 1] - rm); }
     rs += a0 + a1;
   }
-  // column partial (softmax over dim 1) over the 32 rows of this warp
-  float w[32];
+  // column partial (softmax over dim 1): write the sim block back, read it column-per-lane (conflict-free with the
+  // 36-float pitch) and reduce over the 32 rows in registers - no shuffles
+  __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 32; ++j) w[j] = v[j];
-  const float cm = transpose_reduce(w, lane, OpMax());
+  for (int j4 = 0; j4 < 8; ++j4)
+    *reinterpret_cast<float4*>(tb + lane * TBP + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+  __syncwarp();
+  float cm = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float cmj = __shfl_sync(0xffffffffu, cm, j);
-    w[j] = (v[j] > -INFINITY) ? __expf(v[j] - cmj) : 0.f;
+  for (int r = 0; r < 32; ++r) {
+    v[r] = tb[r * TBP + lane];
+    cm = fmaxf(cm, v[r]);
   }
-  const float cs = transpose_reduce(w, lane, OpAdd());
+  float c0s = 0.f, c1s = 0.f;
+  if (cm > -INFINITY) {
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) { c0s += __expf(v[r] - cm); c1s += __expf(v[r + 1] - cm); }
+  }
   const int c = cbase + lane;
-  if (c < p.S) p.colpart[((long long)img * p.S + c) * p.col_parts + m_tile * 4 + q] = make_float2(cm, cs);
+  if (c < p.S) p.colpart[((long long)img * p.S + c) * p.col_parts + m_tile * 4 + q] = make_float2(cm, c0s + c1s);
 }
 
 __device__ __forceinline__ void corr_conf_group(const KParams& p, const float* tb, int lane, int img, int cbase, long long row,
-                                                bool rmasked, unsigned long long& best) {
-  const float2 rst = p.rowstat[row];
+                                                bool row_ok, bool rmasked, unsigned long long& best) {
+  // called by the whole warp (shuffles inside); rows beyond L get rmax = +inf and never produce candidates
+  const float2 rst = row_ok ? p.rowstat[row] : make_float2(INFINITY, 1.f);
   const long long gc0 = (long long)img * p.S + cbase;
   const int ncol = min(32, p.S - cbase);
   // conf = softmax_col * softmax_row <= exp((x - rmax) + (x - cmax)): only entries that can exceed the threshold are
@@ -484,14 +541,13 @@ __device__ __forceinline__ void corr_conf_group(const KParams& p, const float* t
     const float4 t4 = *reinterpret_cast<const float4*>(tb + lane * TBP + j4 * 4);
     xs[j4 * 4] = t4.x; xs[j4 * 4 + 1] = t4.y; xs[j4 * 4 + 2] = t4.z; xs[j4 * 4 + 3] = t4.w;
   }
+  // column maxima of this group: one coalesced load (lane = column), broadcast by shuffle
+  const float my_cmax = (lane < ncol) ? __ldg(&p.colstat[gc0 + lane].x) : INFINITY;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float x = xs[j] * p.sim_scale;
-    float cmax = INFINITY;
-    if (j < ncol) {
-      cmax = __ldg(&p.colstat[gc0 + j].x);
-      if (rmasked || (p.mask1 && p.mask1[gc0 + j] == 0)) x = -1e9f;
-    }
+    const float cmax = __shfl_sync(0xffffffffu, my_cmax, j);
+    if (j < ncol && (rmasked || (p.mask1 && p.mask1[gc0 + j] == 0))) x = -1e9f;
     const float t = (x - rst.x) + (x - cmax);
     cand |= (t > p.thr_log) ? (1u << j) : 0u;
   }
@@ -510,7 +566,7 @@ __device__ __forceinline__ void corr_conf_group(const KParams& p, const float* t
   }
 }
 
-template <int EPI, int OUT, bool kSlowAct>
+template <int EPI, int OUT, bool kSlowAct, bool kLN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ TMaps maps, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -519,12 +575,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   const uint32_t bars = base + p.stages * p.stage_bytes;        // barrier block
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + p.stages * p.stage_bytes + 256);
   float* tbuf = reinterpret_cast<float*>(gen + p.stages * p.stage_bytes + 512);  // [NUM_EPI_WARPS][32][TBP] transpose tiles
+  float* lnstat = tbuf + NUM_EPI_WARPS * 32 * TBP;                                // [2][4 quadrants][2 halves][32 rows]
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
   auto tfull_bar = [&](int b) { return bars + 128u + 8u * b; };
   auto tempty_bar = [&](int b) { return bars + 144u + 8u * b; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (p.cluster == 2) ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi[0]);
@@ -536,7 +594,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(full_bar(s), 1);
-        mbar_init(empty_bar(s), 1);
+        mbar_init(empty_bar(s), (uint32_t)p.cluster);  // released by the MMA warp of every CTA that reads/writes the stage
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(tfull_bar(b), 1);
@@ -551,6 +609,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -562,8 +621,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+      for (int it = tile_first(p); it < tile_count(p); it += tile_step(p)) {
+        const TileCoord tc = decode_tile(p, tile_linear(p, it, cta_rank));
         const int n0 = tc.n_tile * p.bn;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -599,8 +658,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             tma_load_4d(sA + A_TILE_BYTES, &maps.a_lo[view], fb, cb * BK, tc.ow0 + dw, tc.oh0 + dh, tc.img);
           }
           const int bb = (p.mode == 0) ? tc.img : 0;  // weights: one matrix; coarse matching: f1 of the same pair
-          tma_load_3d(sB, &maps.b_hi, fb, bk, n0, bb);
-          tma_load_3d(sB + b_plane, &maps.b_lo, fb, bk, n0, bb);
+          if (p.cluster == 2) {
+            // each CTA of the pair fetches half of the B rows and multicasts them into both CTAs' stage
+            const uint32_t hoff = cta_rank * (b_plane >> 1);
+            const int nh = n0 + (int)cta_rank * (p.bn >> 1);
+            tma_load_3d_mc(sB + hoff, &maps.bh_hi, fb, bk, nh, bb, (uint16_t)3);
+            tma_load_3d_mc(sB + b_plane + hoff, &maps.bh_lo, fb, bk, nh, bb, (uint16_t)3);
+          } else {
+            tma_load_3d(sB, &maps.b_hi, fb, bk, n0, bb);
+            tma_load_3d(sB + b_plane, &maps.b_lo, fb, bk, n0, bb);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -612,7 +679,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;  // chunk counter across tiles: TMEM buffer = cc & 1
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int it = tile_first(p); it < tile_count(p); it += tile_step(p)) {
         int kb = 0;
         for (int ch = 0; ch < p.num_chunks; ++ch, ++cc) {
           const int buf = cc & 1;
@@ -657,7 +724,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
               else umma_f16(tacc, a_hi, b_hi, p.idesc, 1);
               first = false;
             }
-            umma_commit(empty_bar(stage));  // smem stage reusable once every MMA of both passes has read it
+            // smem stage reusable once every MMA of both passes has read it (in both CTAs of a pair)
+            if (p.cluster == 2) umma_commit_mc(empty_bar(stage), (uint16_t)3);
+            else umma_commit(empty_bar(stage));
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
           umma_commit(tfull_bar(buf));      // chunk accumulator complete
@@ -673,7 +742,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     const int half = (warp - 4) >> 2;     // which alternate 32-column groups this warp owns
     const int r_in_tile = q * 32 + lane;  // accumulator row owned by this thread
     uint32_t cc = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int it = tile_first(p); it < tile_count(p); it += tile_step(p)) {
+      const int t = tile_linear(p, it, cta_rank);
       const TileCoord tc = decode_tile(p, t);
       const int n0 = tc.n_tile * p.bn;
       long long row;
@@ -684,13 +754,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         if (EPI != EPI_STORE) row += (long long)tc.img * p.L;  // global row of the batched problem
       } else {
         const int oh = tc.oh0 + r_in_tile / TW, ow = tc.ow0 + r_in_tile % TW;
-        row_ok = oh < p.OH && ow < p.OW;
+        row_ok = oh < p.OH && ow < p.OW && tc.img < p.n_imgs;
         row = ((long long)tc.img * p.OH + oh) * p.OW + ow;
       }
-      if (EPI == EPI_STORE && (OUT & OUT_RESIDUAL) && p.residual) {
-        if (t == (int)blockIdx.x) prefetch_residual(p, tc, lane, q, half);  // first tile: no lead time available
-        const int tn = t + gridDim.x;
-        if (tn < p.num_tiles) prefetch_residual(p, decode_tile(p, tn), lane, q, half);
+      if (EPI == EPI_STORE && (((OUT & OUT_RESIDUAL) && p.residual) || (OUT & OUT_RES_PLANES))) {
+        if (it == tile_first(p)) prefetch_residual(p, tc, lane, q, half);  // first tile: no lead time available
+        const int itn = it + tile_step(p);
+        if (itn < tile_count(p)) prefetch_residual(p, decode_tile(p, tile_linear(p, itn, cta_rank)), lane, q, half);
       }
 
       // ---- drain the chunk accumulators into fp32 registers (round-to-nearest adds)
@@ -748,7 +818,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           if (c0 >= p.bn) break;
           __syncwarp();
           stage_group(tb, lane, acc, gi);
-          if (row_ok) corr_conf_group(p, tb, lane, tc.img, n0 + c0, row, rmasked, best);
+          corr_conf_group(p, tb, lane, tc.img, n0 + c0, row, row_ok, rmasked, best);
         }
         if (row_ok && best) atomicMax(&p.rowbest[row], best);
         continue;
@@ -759,6 +829,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       // global access in store_group() is one contiguous 128-byte (fp32) or 64-byte (fp16) segment per warp
       // instruction.  (Row-per-lane stores cost 32 LSU wavefronts per instruction.)
       float* tb = tbuf + (warp - 4) * (32 * TBP);
+      if constexpr (kLN) {
+        // fused LayerNorm over the full row (N == bn): this thread holds its row's columns of the alternate groups,
+        // the partner warp of the quadrant the others; two-pass statistics exchanged through shared memory
+        // (nn.LayerNorm eps 1e-5, networks/loftr/submodules/transformer.py:32-33; gamma/beta ride in scale/bias).
+        const float inv_n = 1.f / (float)p.N;
+        float* st1 = lnstat + (q * 2) * 32;
+        float* st2 = lnstat + 256 + (q * 2) * 32;
+        float sum = 0.f;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi)
+          if ((gi * 2 + half) * 32 < p.bn) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += acc[gi][j];
+          }
+        st1[half * 32 + lane] = sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float mean = (st1[lane] + st1[32 + lane]) * inv_n;
+        float sq = 0.f;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi)
+          if ((gi * 2 + half) * 32 < p.bn) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float d = acc[gi][j] - mean;
+              sq = fmaf(d, d, sq);
+            }
+          }
+        st2[half * 32 + lane] = sq;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float rstd = 1.f / sqrtf((st2[lane] + st2[32 + lane]) * inv_n + 1e-5f);
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[gi][j] = (acc[gi][j] - mean) * rstd;
+      }
 #pragma unroll 1
       for (int gi = 0; gi < 4; ++gi) {
         const int c0 = (gi * 2 + half) * 32;
@@ -771,9 +876,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     }
   }
 
-  // ---- teardown
+  // ---- teardown (cluster mode: no CTA may exit while its peer can still multicast into it / arrive on its barriers)
   tc_fence_before();
   __syncthreads();
+  if (p.cluster == 2) cluster_sync_all();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -832,6 +938,16 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, co
   GIMB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rank %d, dims %llu %llu %llu)", (int)r, rank,
              (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)(rank > 2 ? gd[2] : 0));
   return 0;
+}
+
+// CTA-pair multicast of the B operand: on (2) by default, GIMB_CLUSTER=1 turns it off
+int cluster_setting() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("GIMB_CLUSTER");
+    v = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  return v;
 }
 
 // k-blocks per in-TMEM accumulation chunk (GIMB_CHUNK_KB overrides the default for experiments)
@@ -949,6 +1065,18 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   p.res_hi = g.residual_planes.hi; p.res_lo = g.residual_planes.lo; p.ldr = g.residual_planes.ld;
 
   p.nb = 1;
+  p.n_imgs = g.mode == 1 ? g.B : 1;
+  p.m_tiles_real = m_tiles;
+  // CTA pairs (cluster of 2) share every B tile through TMA multicast: 1/3 less L2 -> SM operand traffic.  Used when
+  // the layer is big enough to fill the pairs (GIMB_CLUSTER=1 disables).
+  p.cluster = (cluster_setting() == 2 && m_tiles >= 2 * ctx.sm_count && p.bn % 16 == 0 && p.bn >= 32) ? 2 : 1;
+  if (p.cluster == 2) {
+    const int m_even = (m_tiles + 1) / 2 * 2;  // an odd tile count gets one dummy tile (TMA OOB zero fill, masked stores)
+    p.num_tiles = m_even * p.n_tiles;
+    const uint64_t Kw = g.mode == 0 ? (uint64_t)g.K1 + g.K2 : (uint64_t)g.KH * g.KW * g.ldk;
+    GIMB_TRY(rows_map(&maps.bh_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn / 2));
+    GIMB_TRY(rows_map(&maps.bh_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn / 2));
+  }
   const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
   const bool slow = g.act0 >= ACT_ELU1 || g.act1 >= ACT_ELU1 || g.row_mask != nullptr;
   const bool f32 = g.out_f32 != nullptr, planes = g.out.hi != nullptr, res = g.residual != nullptr;
@@ -956,19 +1084,35 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   GIMB_CHECK(!(res && resp), "umma_gemm: residual given twice");
   if (resp) GIMB_CHECK(g.residual_planes.lo && g.residual_planes.ld % 8 == 0 && g.residual_planes.ld >= g.N, "umma_gemm: bad residual planes");
   GIMB_CHECK(g.out.h8 == nullptr, "umma_gemm: the GEMM epilogue does not produce the h8 plane");
-  const int grid = std::min(p.num_tiles, ctx.sm_count);
+  int grid = std::min(p.num_tiles, ctx.sm_count);
+  if (p.cluster == 2) grid = std::min(p.num_tiles, ctx.sm_count / 2 * 2);
   cudaError_t aerr = cudaSuccess;
-#define GIMB_LAUNCH_VARIANT(OUTV, SLOWV)                                                                          \
+  cudaLaunchConfig_t lcfg = {};
+  cudaLaunchAttribute lattr[1];
+  lcfg.gridDim = dim3(grid); lcfg.blockDim = dim3(NUM_THREADS); lcfg.dynamicSmemBytes = smem; lcfg.stream = ctx.stream;
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = p.cluster; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
+  lcfg.attrs = lattr; lcfg.numAttrs = 1;
+#define GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, LNV)                                                                   \
   do {                                                                                                            \
     static bool done = false;                                                                                     \
     if (!done) {                                                                                                  \
-      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  SMEM_LIMIT);                                                                    \
+      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV>,                                  \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);                      \
       done = true;                                                                                                \
     }                                                                                                             \
-    umma_gemm_kernel<EPI_STORE, OUTV, SLOWV><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);                   \
+    if (aerr == cudaSuccess) aerr = cudaLaunchKernelEx(&lcfg, umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV>, maps, p); \
   } while (0)
-  if (resp) {
+#define GIMB_LAUNCH_VARIANT(OUTV, SLOWV) GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, false)
+  if (g.layernorm) {
+    GIMB_CHECK(g.N == p.bn && g.N % 64 == 0 && g.scale && !slow && !resp, "umma_gemm: fused LayerNorm needs N == tile N, gamma/beta");
+    if (!f32 && planes && !res) GIMB_LAUNCH_VARIANT_LN(OUT_PLANES, false, true);
+    else if (f32 && planes && res) GIMB_LAUNCH_VARIANT_LN(OUT_F32 | OUT_PLANES | OUT_RESIDUAL, false, true);
+    else {
+      set_error("umma_gemm: unsupported fused-LayerNorm output combination");
+      return 1;
+    }
+  } else if (resp) {
     if (!f32 && planes && !slow) GIMB_LAUNCH_VARIANT(OUT_PLANES | OUT_RES_PLANES, false);
     else {
       set_error("umma_gemm: residual planes are supported for plane-only output");
@@ -984,6 +1128,7 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     return 1;
   }
 #undef GIMB_LAUNCH_VARIANT
+#undef GIMB_LAUNCH_VARIANT_LN
   GIMB_CUDA(aerr);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
@@ -1012,6 +1157,7 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   p.M = c.L;
   const int m_tiles = cdiv(c.L, BM);
   p.nb = c.N; p.L = c.L; p.S = c.S;
+  p.cluster = 1; p.n_imgs = 1; p.m_tiles_real = m_tiles;
   p.tiles_per_batch = m_tiles * p.n_tiles;
   p.num_tiles = c.N * p.tiles_per_batch;
   GIMB_TRY(rows_map(&maps.a_hi[0], c.f0.hi, c.C, c.L, c.f0.ld, BM, c.N));
@@ -1037,15 +1183,15 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
   static bool attr_done = false;
   if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = std::min(p.num_tiles, ctx.sm_count);
   if (pass == 0)
-    umma_gemm_kernel<EPI_CORR_STATS, 0, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_STATS, 0, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   else
-    umma_gemm_kernel<EPI_CORR_CONF, 0, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_CONF, 0, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;

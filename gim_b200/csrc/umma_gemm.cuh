@@ -47,6 +47,7 @@ struct UmmaGemm {
   const uint8_t* row_mask = nullptr;
   int act0 = ACT_NONE, act1 = ACT_NONE, act_split = 1 << 30;
   float div = 1.f;
+  bool layernorm = false;            // LayerNorm(eps 1e-5) of each output row BEFORE scale (= gamma) / bias (= beta) / residual
   float* out_f32 = nullptr;          // [M, N] pitch N (optional)
   SplitPlanes out;                   // optional fp16 planes (hi, lo[, h8]); pad channels [N, ld) are zeroed
 };

@@ -14,6 +14,9 @@ LAYERS = [
     ("l1.x.c2 3x3 64->64", B, 240, 320, 64, 0, 64, 3, 1, 1 | 8, 1),
     ("l1.0.ds 1x1 64->256 f32", B, 240, 320, 64, 0, 256, 1, 1, 1 | 4, 0),
     ("l1.x.c3 1x1 64->256 +res", B, 240, 320, 64, 0, 256, 1, 1, 1 | 2 | 4 | 8, 1),
+    ("l1.x.c3p 1x1 64->256 +res planes", B, 240, 320, 64, 0, 256, 1, 1, 1 | 8 | 16, 1),
+    ("l2.x.c3p 1x1 128->512 +res planes", B, 120, 160, 128, 0, 512, 1, 1, 1 | 8 | 16, 1),
+    ("l3.x.c3p 1x1 256->1024 +res planes", B, 60, 80, 256, 0, 1024, 1, 1, 1 | 8 | 16, 1),
     ("l1.x.c1 1x1 256->64", B, 240, 320, 256, 0, 64, 1, 1, 1 | 8, 1),
     ("l2.0.c2 3x3s2 128->128", B, 240, 320, 128, 0, 128, 3, 2, 1 | 8, 1),
     ("l2.x.c2 3x3 128->128", B, 120, 160, 128, 0, 128, 3, 1, 1 | 8, 1),
@@ -46,7 +49,7 @@ def main():
         M = b * oh * ow
         K = k * k * (c1 + c2)
         gflop = 2.0 * M * co * K / 1e9
-        byt = b * h * w * (c1 + c2) * 4 + M * co * ((4 if flags & 2 else 0) + (4 if flags & 4 else 0) + (4 if flags & 8 else 0))
+        byt = b * h * w * (c1 + c2) * 4 + M * co * ((4 if flags & 2 else 0) + (4 if flags & 4 else 0) + (4 if flags & 8 else 0) + (4 if flags & 16 else 0))
         t = ms.value / 1e3
         print(f"{name:34s} {ms.value:8.3f} ms  alg {gflop / t / 1e3:7.1f} TF/s  mma {3 * gflop / t / 1e3:7.1f} TF/s  "
               f"hbm {byt / t / 1e9:7.0f} GB/s", flush=True)
