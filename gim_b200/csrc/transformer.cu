@@ -290,7 +290,9 @@ int linear_attention(Ctx& ctx, const float* q, const float* kv, int B, int L, in
   const PlanesDev sp = planes ? dev(*planes) : PlanesDev{nullptr, nullptr, nullptr, 0};
   GIMB_CHECK(C == nhead * 32, "linear_attention: coarse flavour needs head dim 32");
   const int BH = B * nhead;
-  int nsplit = std::max(1, std::min(cdiv(ctx.sm_count * 4, BH), cdiv(S, 4 * KV_CHUNK)));
+  // fixed split of the S reduction (a function of S only): results do not depend on the batch size, so a pair gives
+  // bit-identical features whether it is processed alone or in a batch
+  int nsplit = std::max(1, std::min(32, cdiv(S, 16 * KV_CHUNK)));
   size_t mark = ctx.arena.mark();
   float* part = ctx.arena.alloc<float>((size_t)BH * nsplit * KV_STRIDE);
   float* kvf = ctx.arena.alloc<float>((size_t)BH * KV_STRIDE);

@@ -40,13 +40,14 @@ constexpr int TBP = 36;  // pitch (floats) of the per-warp 32 x 32 transpose til
 constexpr int SMEM_EXTRA = 1024 /*alignment slack*/ + 512 /*barriers*/ + NUM_EPI_WARPS * 32 * TBP * 4 /*transpose tiles*/ +
                            2 * NUM_EPI_WARPS * 32 * 4 /*LayerNorm row statistics*/;
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_COLS = 256;
+constexpr int ACC_COLS = 256;  // accumulator buffer width for tiles wider than 128 columns (2 buffers); narrower tiles use 4 x 128
 
 struct TMaps {
   CUtensorMap a_hi[4], a_lo[4];  // mode 1 stride 2: four phase views; otherwise index 0
   CUtensorMap a2_hi, a2_lo;      // mode 0 concat source
   CUtensorMap b_lo, b_hi;
   CUtensorMap bh_lo, bh_hi;      // cluster mode: half-height boxes (bn / 2 rows) of the B planes
+  CUtensorMap r_hi, r_lo;        // residual planes (row mode): used for bulk L2 prefetch of the next tile's identity block
 };
 
 struct KParams {
@@ -59,6 +60,8 @@ struct KParams {
   int N, n_tiles, bn;
   int stages, stage_bytes;
   int num_tiles, num_kb, num_chunks, chunk_kb;
+  int acc_cols, nbuf_log2;  // TMEM ring: 2 x 256 or 4 x 128 columns
+  int res_stage;     // 1: residual planes are staged per warp through smem with cp.async (OUT_RES_PLANES kernels)
   int cluster;       // 1, or 2: CTA pairs share every B (weight) tile through TMA multicast
   int m_tiles_real;  // cluster mode: m tiles that exist (the pair grid may carry one dummy tile)
   int n_imgs;
@@ -155,6 +158,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk L2 prefetch of one box (no shared-memory destination)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -282,7 +290,8 @@ enum { OUT_F32 = 1, OUT_PLANES = 2, OUT_RESIDUAL = 4, OUT_RES_PLANES = 8 };  // 
 // issue latency, i.e. by instructions per element: the scalar (lane = column) form needed ~60 per 32 elements.
 template <int OUT, bool kSlowAct>
 __device__ __forceinline__ void store_rows(const KParams& p, const float* tb, int lane, int cbase, long long g0,
-                                           long long rowjump, unsigned valid, unsigned rmask_bits) {
+                                           long long rowjump, unsigned valid, unsigned rmask_bits, const uint2 (&pre_rh)[8],
+                                           const uint2 (&pre_rl)[8], bool use_pre) {
   const int rsub = lane >> 3, cq = lane & 7;
   const int c = cbase + cq * 4;            // this lane's 4 columns c .. c+3 (N, act_split, ldp are multiples of 4)
   const bool c_ok = c < p.N;
@@ -330,8 +339,13 @@ __device__ __forceinline__ void store_rows(const KParams& p, const float* tb, in
       const int rr = it * 4 + rsub;
       const long long grow = g0 + (rr >> 4) * rowjump + (rr & 15);
       const bool ld = c_ok && ((valid >> rr) & 1u);
-      rh[it] = ld ? *reinterpret_cast<const uint2*>(p.res_hi + grow * lr64 + c) : make_uint2(0u, 0u);
-      rl[it] = ld ? *reinterpret_cast<const uint2*>(p.res_lo + grow * lr64 + c) : make_uint2(0u, 0u);
+      if (use_pre) {  // staged by cp.async and already in registers (zero-filled where invalid)
+        rh[it] = pre_rh[it];
+        rl[it] = pre_rl[it];
+      } else {
+        rh[it] = ld ? *reinterpret_cast<const uint2*>(p.res_hi + grow * lr64 + c) : make_uint2(0u, 0u);
+        rl[it] = ld ? *reinterpret_cast<const uint2*>(p.res_lo + grow * lr64 + c) : make_uint2(0u, 0u);
+      }
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -427,8 +441,43 @@ __device__ __forceinline__ void prefetch_residual(const KParams& p, const TileCo
   }
 }
 
+constexpr int RES_BUF_BYTES = 4096;  // one 32 x 32 block of both residual planes
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// issue the cp.async copies of the residual block (rows of this warp's quadrant, columns cbase .. cbase+31) into `buf`
+__device__ __forceinline__ void issue_residual_block(const KParams& p, const TileCoord& tc, int lane, int q, int cbase,
+                                                     uint8_t* buf) {
+  long long g0, rowjump;
+  int oh = 0, ow = 0;
+  if (p.mode == 0) {
+    g0 = (long long)tc.m_tile * BM + q * 32;
+    rowjump = 16;
+  } else {
+    oh = tc.oh0 + q * 2; ow = tc.ow0;
+    g0 = ((long long)tc.img * p.OH + oh) * p.OW + ow;
+    rowjump = p.OW;
+  }
+  const uint32_t sbuf = smem_u32(buf);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + 32 * i;       // 256 x 16-byte pieces: [plane][row][4 segments of 8 halves]
+    const int plane = idx >> 7, row = (idx >> 2) & 31, seg = idx & 3;
+    bool ok;
+    if (p.mode == 0) ok = g0 + row < p.M;
+    else ok = (oh + (row >> 4) < p.OH) && (ow + (row & 15) < p.OW) && tc.img < p.n_imgs;
+    const int c = cbase + seg * 8;
+    ok = ok && c < p.N;
+    const long long grow = g0 + (row >> 4) * rowjump + (row & 15);
+    const __half* src = (plane ? p.res_lo : p.res_hi) + (ok ? grow * (long long)p.ldr + c : 0);
+    cp_async16(sbuf + plane * 2048 + row * 64 + seg * 16, src, ok ? 16 : 0);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <int OUT, bool kSlowAct>
-__device__ __forceinline__ void store_group(const KParams& p, const float* tb, int lane, int q, const TileCoord& tc, int cbase) {
+__device__ __forceinline__ void store_group(const KParams& p, const float* tb, int lane, int q, const TileCoord& tc, int cbase,
+                                            const uint2 (&pre_rh)[8], const uint2 (&pre_rl)[8], bool use_pre) {
   long long g0, rowjump;
   bool my_ok;  // validity of row rr == lane
   if (p.mode == 0) {
@@ -447,7 +496,7 @@ __device__ __forceinline__ void store_group(const KParams& p, const float* tb, i
     const long long grow = g0 + (lane >> 4) * rowjump + (lane & 15);
     rmask_bits = __ballot_sync(0xffffffffu, my_ok && p.row_mask[grow] != 0);
   }
-  store_rows<OUT, kSlowAct>(p, tb, lane, cbase, g0, rowjump, valid, rmask_bits);
+  store_rows<OUT, kSlowAct>(p, tb, lane, cbase, g0, rowjump, valid, rmask_bits, pre_rh, pre_rl, use_pre);
 }
 
 // Copy one of the four register-resident 32-column accumulator groups into the warp's smem tile.  The group loop in
@@ -576,10 +625,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + p.stages * p.stage_bytes + 256);
   float* tbuf = reinterpret_cast<float*>(gen + p.stages * p.stage_bytes + 512);  // [NUM_EPI_WARPS][32][TBP] transpose tiles
   float* lnstat = tbuf + NUM_EPI_WARPS * 32 * TBP;                                // [2][4 quadrants][2 halves][32 rows]
+  // OUT_RES_PLANES: per epilogue warp one 4 KB buffer ([plane hi|lo][32 rows][32 halves]) for the residual block of the
+  // next 32-column group, filled with cp.async one group ahead (the identity loads were latency-bound)
+  uint8_t* resbuf = reinterpret_cast<uint8_t*>(lnstat + 2 * NUM_EPI_WARPS * 32);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
-  auto tfull_bar = [&](int b) { return bars + 128u + 8u * b; };
-  auto tempty_bar = [&](int b) { return bars + 144u + 8u * b; };
+  auto tfull_bar = [&](int b) { return bars + 128u + 8u * b; };   // up to 4 accumulator buffers
+  auto tempty_bar = [&](int b) { return bars + 160u + 8u * b; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (p.cluster == 2) ? cluster_ctarank() : 0u;
@@ -596,7 +648,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         mbar_init(full_bar(s), 1);
         mbar_init(empty_bar(s), (uint32_t)p.cluster);  // released by the MMA warp of every CTA that reads/writes the stage
       }
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < 4; ++b) {
         mbar_init(tfull_bar(b), 1);
         mbar_init(tempty_bar(b), NUM_EPI_WARPS);
       }
@@ -624,6 +676,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       for (int it = tile_first(p); it < tile_count(p); it += tile_step(p)) {
         const TileCoord tc = decode_tile(p, tile_linear(p, it, cta_rank));
         const int n0 = tc.n_tile * p.bn;
+        if ((OUT & OUT_RES_PLANES) && p.res_stage && p.mode == 0) {
+          // identity block of the NEXT tile (and of the very first one) -> L2, a whole tile ahead of its consumer: the
+          // epilogue's cp.async staging then only sees L2 latency (DRAM latency under this read+write load is ~3 us)
+          const int itn = it + tile_step(p);
+          for (int pass = (it == tile_first(p)) ? 0 : 1; pass < 2; ++pass) {
+            const int itx = pass == 0 ? it : itn;
+            if (itx >= tile_count(p)) break;
+            const TileCoord tx = decode_tile(p, tile_linear(p, itx, cta_rank));
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+              tma_prefetch_l2_3d(&maps.r_hi, tx.n_tile * p.bn + c0, tx.m_tile * BM, 0);
+              tma_prefetch_l2_3d(&maps.r_lo, tx.n_tile * p.bn + c0, tx.m_tile * BM, 0);
+            }
+          }
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sA = base + stage * p.stage_bytes;
@@ -678,14 +744,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t cc = 0;  // chunk counter across tiles: TMEM buffer = cc & 1
+      uint32_t cc = 0;  // chunk counter across tiles: TMEM buffer = cc mod (number of buffers)
       for (int it = tile_first(p); it < tile_count(p); it += tile_step(p)) {
         int kb = 0;
         for (int ch = 0; ch < p.num_chunks; ++ch, ++cc) {
-          const int buf = cc & 1;
-          mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
+          const int buf = cc & ((1u << p.nbuf_log2) - 1u);
+          mbar_wait(tempty_bar(buf), ((cc >> p.nbuf_log2) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + buf * ACC_COLS;
+          const uint32_t tacc = tmem_base + buf * p.acc_cols;
           const int kb_end = min(p.num_kb, kb + p.chunk_kb);
           // pass 1 over the chunk's stages: the two cross terms  D  = sum_k (A_hi*B_lo + A_lo*B_hi)      [lo = 2^8 * residual]
           // pass 2 over the same stages:    the main term        D  = sum_k A_hi*B_hi + 2^-8 * D         (scale-input-d = 8
@@ -757,7 +823,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         row_ok = oh < p.OH && ow < p.OW && tc.img < p.n_imgs;
         row = ((long long)tc.img * p.OH + oh) * p.OW + ow;
       }
-      if (EPI == EPI_STORE && (((OUT & OUT_RESIDUAL) && p.residual) || (OUT & OUT_RES_PLANES))) {
+      if (EPI == EPI_STORE && (((OUT & OUT_RESIDUAL) && p.residual) || ((OUT & OUT_RES_PLANES) && !p.res_stage))) {
         if (it == tile_first(p)) prefetch_residual(p, tc, lane, q, half);  // first tile: no lead time available
         const int itn = it + tile_step(p);
         if (itn < tile_count(p)) prefetch_residual(p, decode_tile(p, tile_linear(p, itn, cta_rank)), lane, q, half);
@@ -770,10 +836,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[gi][j] = 0.f;
       for (int ch = 0; ch < p.num_chunks; ++ch, ++cc) {
-        const int buf = cc & 1;
-        mbar_wait(tfull_bar(buf), (cc >> 1) & 1);
+        const int buf = cc & ((1u << p.nbuf_log2) - 1u);
+        mbar_wait(tfull_bar(buf), (cc >> p.nbuf_log2) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * p.acc_cols;
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
           const int c0 = (gi * 2 + half) * 32;
@@ -864,14 +930,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[gi][j] = (acc[gi][j] - mean) * rstd;
       }
+      const bool staged = (OUT & OUT_RES_PLANES) && p.res_stage;
+      uint8_t* rb = resbuf + (warp - 4) * RES_BUF_BYTES;
+      if (staged) issue_residual_block(p, tc, lane, q, n0 + half * 32, rb);  // group 0 of this warp
 #pragma unroll 1
       for (int gi = 0; gi < 4; ++gi) {
         const int c0 = (gi * 2 + half) * 32;
         if (c0 >= p.bn) break;  // warp-uniform
+        uint2 rh[8], rl[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) { rh[it] = make_uint2(0u, 0u); rl[it] = make_uint2(0u, 0u); }
+        if (staged) {
+          // the residual block of this group was requested a whole group (or the drain) ago: pull it into registers,
+          // then reuse the buffer for the next group's request
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          const int rsub = lane >> 3, cq = lane & 7;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            rh[it] = *reinterpret_cast<const uint2*>(rb + (it * 4 + rsub) * 64 + cq * 8);
+            rl[it] = *reinterpret_cast<const uint2*>(rb + 2048 + (it * 4 + rsub) * 64 + cq * 8);
+          }
+          __syncwarp();
+          const int c1 = ((gi + 1) * 2 + half) * 32;
+          if (gi + 1 < 4 && c1 < p.bn) issue_residual_block(p, tc, lane, q, n0 + c1, rb);
+        }
         __syncwarp();
         stage_group(tb, lane, acc, gi);
         __syncwarp();
-        store_group<OUT, kSlowAct>(p, tb, lane, q, tc, n0 + c0);
+        store_group<OUT, kSlowAct>(p, tb, lane, q, tc, n0 + c0, rh, rl, staged);
       }
     }
   }
@@ -1050,7 +1137,19 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn));
   }
   p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * BK * 2;
-  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - SMEM_EXTRA) / p.stage_bytes);
+  // the planes-residual epilogue stages the identity block through smem (8 warps x 4 KB) when the ring still
+  // keeps >= 3 stages (or the whole K + 1) beside it
+  const int res_bytes = NUM_EPI_WARPS * 4096;
+  p.res_stage = 0;
+  if (g.residual_planes.hi) {
+    const int st = (SMEM_LIMIT - SMEM_EXTRA - res_bytes) / p.stage_bytes;
+    if (st >= std::min(3, p.num_kb + 1)) p.res_stage = 1;
+  }
+  if (p.res_stage && g.mode == 0) {
+    GIMB_TRY(rows_map(&maps.r_hi, g.residual_planes.hi, g.N, g.M, g.residual_planes.ld, BM));
+    GIMB_TRY(rows_map(&maps.r_lo, g.residual_planes.lo, g.N, g.M, g.residual_planes.ld, BM));
+  }
+  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - SMEM_EXTRA - (p.res_stage ? res_bytes : 0)) / p.stage_bytes);
   p.stages = std::max(2, std::min(p.stages, std::max(3, p.num_kb + 1)));
   p.num_tiles = m_tiles * p.n_tiles;
   // K <= 128: one in-TMEM chunk (24 accumulation steps keep the truncation bias at the fp32-FFMA level and save a
@@ -1059,6 +1158,8 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   p.chunk_kb = std::max(1, std::min(p.chunk_kb, p.stages - 1));  // a chunk's stages stay resident for both MMA passes
   p.num_chunks = cdiv(p.num_kb, p.chunk_kb);
   p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+  p.acc_cols = p.bn <= 128 ? 128 : ACC_COLS;
+  p.nbuf_log2 = p.bn <= 128 ? 2 : 1;
   p.scale = g.scale; p.bias = g.bias; p.residual = g.residual; p.row_mask = g.row_mask;
   p.act0 = g.act0; p.act1 = g.act1; p.act_split = g.act_split; p.div = g.div;
   p.out_f32 = g.out_f32; p.out_hi = g.out.hi; p.out_lo = g.out.lo; p.out_h8 = g.out.h8; p.ldp = g.out.ld;
@@ -1077,7 +1178,7 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     GIMB_TRY(rows_map(&maps.bh_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn / 2));
     GIMB_TRY(rows_map(&maps.bh_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn / 2));
   }
-  const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
+  const int smem = p.stages * p.stage_bytes + SMEM_EXTRA + (p.res_stage ? res_bytes : 0);
   const bool slow = g.act0 >= ACT_ELU1 || g.act1 >= ACT_ELU1 || g.row_mask != nullptr;
   const bool f32 = g.out_f32 != nullptr, planes = g.out.hi != nullptr, res = g.residual != nullptr;
   const bool resp = g.residual_planes.hi != nullptr;
@@ -1135,8 +1236,19 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   return 0;
 }
 
+// N-tile width of the correlation sweeps: 128 -> four TMEM accumulator buffers, the MMA warp runs a whole tile ahead of
+// the (expensive) statistics epilogue; 256 -> two buffers, half as many tiles (GIMB_CORR_BN overrides)
+int corr_bn() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("GIMB_CORR_BN");
+    v = (e && atoi(e) == 256) ? 256 : 128;
+  }
+  return v;
+}
+
 void umma_corr_parts(int L, int S, int* row_parts, int* col_parts) {
-  *row_parts = cdiv(S, 256) * 2;
+  *row_parts = cdiv(S, corr_bn()) * 2;
   *col_parts = cdiv(L, BM) * 4;
 }
 
@@ -1149,9 +1261,9 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   memset(&maps, 0, sizeof(maps));
   p.mode = 0;
   p.N = c.S;
-  p.n_tiles = cdiv(c.S, 256);
-  p.bn = 256;
-  if (c.S < 256) p.bn = cdiv(c.S, 16) * 16;
+  p.bn = corr_bn();
+  p.n_tiles = cdiv(c.S, p.bn);
+  if (c.S < p.bn) p.bn = cdiv(c.S, 16) * 16;
   p.K1 = c.C; p.cb1 = c.C / BK; p.cb2 = 0; p.num_kb = p.cb1;
   p.KH = p.KW = 1; p.stride = 1; p.pad = 0;
   p.M = c.L;
@@ -1169,6 +1281,8 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   p.chunk_kb = std::max(1, std::min(chunk_kb_setting(), p.stages - 1));
   p.num_chunks = cdiv(p.num_kb, p.chunk_kb);
   p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+  p.acc_cols = p.bn <= 128 ? 128 : ACC_COLS;
+  p.nbuf_log2 = p.bn <= 128 ? 2 : 1;
   p.mask0 = c.mask0; p.mask1 = c.mask1;
   p.inv_c = 1.f / (float)c.C;
   p.temperature = c.temperature;

@@ -93,3 +93,27 @@ def test_errors_are_loud(model):
     c = torch.zeros(1, 3, 100, 128, device="cuda")
     with pytest.raises(RuntimeError):
         model(dict(color0=c, color1=c, image0=c, image1=c))  # 100 is not a multiple of 8
+
+
+def test_batch_consistency_and_fine_chunking(model):
+    """Pairs are independent: a batch of 6 pairs (M > 16384, so the fine stage runs in more than one chunk) must give
+    exactly the rows that three batches of 2 give (size-independent property at the bench resolution)."""
+    from gim_b200 import synth
+    c0, c1 = synth.make_pairs(6, 480, 640, first=0)
+    big = dict(color0=c0.cuda(), color1=c1.cuda(), image0=c0, image1=c1)
+    model(big)
+    assert big["b_ids"].numel() > 16384, "workload too easy to exercise the chunk loop"
+    off = 0
+    for k in range(0, 6, 2):
+        d = dict(color0=c0[k:k + 2].cuda(), color1=c1[k:k + 2].cuda(), image0=c0[k:k + 2], image1=c1[k:k + 2])
+        model(d)
+        m = d["b_ids"].numel()
+        sl = slice(off, off + m)
+        assert torch.equal(big["b_ids"][sl], d["b_ids"] + k)
+        for key in ("i_ids", "j_ids", "mconf", "mkpts0_f", "mkpts1_f", "expec_f"):
+            assert torch.equal(big[key][sl], d[key]), key
+        off += m
+    assert off == big["b_ids"].numel()
+    # ordered by (b, i) like torch.where
+    key = big["b_ids"] * 4800 + big["i_ids"]
+    assert bool((key[1:] > key[:-1]).all())

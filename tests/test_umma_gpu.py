@@ -86,6 +86,9 @@ SHAPES = [
     (1, 60, 80, 256, 256, 3, 1, dict(bn=True, act="relu")),                 # K = 2304
     (1, 1000, 1, 256, 512, 1, 1, dict(act="elu1", act1="divs", split=256, div=4800.0, mask=True, planes=False)),  # kv projection (fp32 out)
     (1, 777, 1, 128, 128, 1, 1, dict(act="elu1", mask=True, planes=False)),  # fine q projection (fp32 out)
+    # >= 2 x 148 m-tiles: the CTA-pair path (TMA multicast of the weight tile), odd tile count -> one dummy tile
+    (1, 38005, 1, 256, 256, 1, 1, dict(bn=True, act="relu", planes=False)),
+    (3, 120, 160, 64, 64, 3, 1, dict(bn=True, act="relu", planes=False)),   # conv patches in CTA-pair mode (450 tiles)
 ]
 
 

@@ -15,6 +15,7 @@ LAYERS = [
     ("l1.0.ds 1x1 64->256 f32", B, 240, 320, 64, 0, 256, 1, 1, 1 | 4, 0),
     ("l1.x.c3 1x1 64->256 +res", B, 240, 320, 64, 0, 256, 1, 1, 1 | 2 | 4 | 8, 1),
     ("l1.x.c3p 1x1 64->256 +res planes", B, 240, 320, 64, 0, 256, 1, 1, 1 | 8 | 16, 1),
+    ("l1.x.c3n 1x1 64->256 planes, no res", B, 240, 320, 64, 0, 256, 1, 1, 1 | 8, 1),
     ("l2.x.c3p 1x1 128->512 +res planes", B, 120, 160, 128, 0, 512, 1, 1, 1 | 8 | 16, 1),
     ("l3.x.c3p 1x1 256->1024 +res planes", B, 60, 80, 256, 0, 1024, 1, 1, 1 | 8 | 16, 1),
     ("l1.x.c1 1x1 256->64", B, 240, 320, 256, 0, 64, 1, 1, 1 | 8, 1),
