@@ -17,6 +17,7 @@
 // Tile: BM = 128 output rows (mode 0: consecutive rows; mode 1: an 8 x 16 pixel patch of one image),
 //       BN = whole N up to 256 (rounded to 16), BK = 32 fp16 (64-byte rows).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -47,7 +48,9 @@ struct TMaps {
   CUtensorMap a2_hi, a2_lo;      // mode 0 concat source
   CUtensorMap b_lo, b_hi;
   CUtensorMap bh_lo, bh_hi;      // cluster mode: half-height boxes (bn / 2 rows) of the B planes
-  CUtensorMap r_hi, r_lo;        // residual planes (row mode): used for bulk L2 prefetch of the next tile's identity block
+  CUtensorMap r_hi, r_lo;        // residual planes: boxes of 32 channels x 32 rows (one epilogue warp's block)
+  CUtensorMap r_f32;             // fp32 residual, same blocks (SWIZZLE_128B)
+  CUtensorMap o_hi, o_lo, o_f32; // outputs, same blocks: written with bulk tensor stores from the warp's staging tile
 };
 
 struct KParams {
@@ -61,7 +64,8 @@ struct KParams {
   int stages, stage_bytes;
   int num_tiles, num_kb, num_chunks, chunk_kb;
   int acc_cols, nbuf_log2;  // TMEM ring: 2 x 256 or 4 x 128 columns
-  int res_stage;     // 1: residual planes are staged per warp through smem with cp.async (OUT_RES_PLANES kernels)
+  int res_stage;     // legacy epilogue, 1: residual planes are staged per warp through smem with cp.async
+  int stg_off;       // TMA epilogue: byte offset (from the 1024-aligned smem base) of the per-warp staging tiles
   int cluster;       // 1, or 2: CTA pairs share every B (weight) tile through TMA multicast
   int m_tiles_real;  // cluster mode: m tiles that exist (the pair grid may carry one dummy tile)
   int n_imgs;
@@ -159,6 +163,21 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// bulk tensor stores (shared -> global, clipped at the tensor extents) and their completion tracking
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // bulk L2 prefetch of one box (no shared-memory destination)
 __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
@@ -516,6 +535,189 @@ __device__ __forceinline__ void stage_group(float* tb, int lane, const float (&a
 #undef GIMB_STAGE
 }
 
+
+// =========================================================================================== TMA epilogue
+// Row-per-lane epilogue: the accumulator block arrives with TMEM lane = row, and that is also how it leaves.  Each
+// epilogue warp owns one staging tile per tensor ([32 rows][32 channels]; SWIZZLE_64B for the two fp16 planes,
+// SWIZZLE_128B for fp32) in shared memory: the lane writes its own row with 128-bit stores (the swizzle spreads every
+// quarter-warp over all 32 banks) and ONE bulk tensor store per tensor moves the block to global memory - no
+// transposition round trip, no per-row address arithmetic or predicates (the tensor map clips rows / channels that
+// fall outside the tensor), no LSU store traffic.  The residual block comes in the same way (bulk tensor load
+// signalled on a per-warp mbarrier) and is requested one block ahead of its use - also across tile boundaries - so
+// its DRAM latency hides behind a whole block of work.
+constexpr int STG_BLOCK = 4096;  // bytes of one staged 32 x 32 block (fp32, or both fp16 planes back to back)
+template <int OUT>
+struct StageLayout {
+  static constexpr bool kRes = (OUT & (OUT_RESIDUAL | OUT_RES_PLANES)) != 0;
+  static constexpr int off_res = 0;
+  static constexpr int off_f32 = kRes ? STG_BLOCK : 0;
+  static constexpr int off_pl = off_f32 + ((OUT & OUT_F32) ? STG_BLOCK : 0);
+  static constexpr int bytes = off_pl + ((OUT & OUT_PLANES) ? STG_BLOCK : 0);
+};
+__device__ __forceinline__ uint32_t sw64_off(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// lane 0 of the warp: ask for the residual block (rows of quadrant q of tile tc, channels c .. c+31)
+template <int OUT>
+__device__ __forceinline__ void request_residual(const KParams& p, const TMaps& maps, uint32_t dst, uint32_t bar,
+                                                 const TileCoord& tc, int q, int c) {
+  mbar_expect_tx(bar, STG_BLOCK);
+  if (p.mode == 0) {
+    const int r0 = tc.m_tile * BM + q * 32;
+    if (OUT & OUT_RES_PLANES) {
+      tma_load_3d(dst, &maps.r_hi, bar, c, r0, 0);
+      tma_load_3d(dst + STG_BLOCK / 2, &maps.r_lo, bar, c, r0, 0);
+    } else {
+      tma_load_3d(dst, &maps.r_f32, bar, c, r0, 0);
+    }
+  } else {
+    const int oh = tc.oh0 + q * 2;
+    if (OUT & OUT_RES_PLANES) {
+      tma_load_4d(dst, &maps.r_hi, bar, c, tc.ow0, oh, tc.img);
+      tma_load_4d(dst + STG_BLOCK / 2, &maps.r_lo, bar, c, tc.ow0, oh, tc.img);
+    } else {
+      tma_load_4d(dst, &maps.r_f32, bar, c, tc.ow0, oh, tc.img);
+    }
+  }
+}
+
+// One 32 x 32 block of the store epilogue, lane = row: v[j] is the (LayerNorm-ed) accumulator of channel c + j.
+template <int OUT, bool kSlowAct>
+__device__ __forceinline__ void finish_block(const KParams& p, const TMaps& maps, float (&v)[32], uint32_t wb, uint32_t rbar,
+                                             uint32_t& rphase, bool has_res, int lane, int q, const TileCoord& tc, int c,
+                                             bool keep, bool have_next, const TileCoord& tcn, int cn) {
+  using SL = StageLayout<OUT>;
+  // ---- per-channel affine (folded BatchNorm / bias / LayerNorm gamma, beta); channels >= N give exactly 0
+  if (p.scale) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), bi = sc;
+      if (c + 4 * k < p.N) {
+        sc = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4 * k));
+        bi = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4 * k));
+      }
+      v[4 * k + 0] = fmaf(v[4 * k + 0], sc.x, bi.x);
+      v[4 * k + 1] = fmaf(v[4 * k + 1], sc.y, bi.y);
+      v[4 * k + 2] = fmaf(v[4 * k + 2], sc.z, bi.z);
+      v[4 * k + 3] = fmaf(v[4 * k + 3], sc.w, bi.w);
+      // keeps the 16 parameter loads from being hoisted into one 64-register burst (the accumulate path already
+      // holds 128 accumulator registers)
+      if (k & 1) asm volatile("" ::: "memory");
+    }
+  }
+  // ---- residual block (requested one block ago)
+  if (SL::kRes && has_res) {
+    mbar_wait(rbar, rphase);
+    rphase ^= 1u;
+    if (OUT & OUT_RES_PLANES) {
+      // identity carried as fp16 planes: x = hi + lo * 2^-8 (exact to 2^-22 relative)
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const uint4 h = lds128(wb + SL::off_res + sw64_off(lane, ch));
+        const uint4 l = lds128(wb + SL::off_res + STG_BLOCK / 2 + sw64_off(lane, ch));
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+          v[ch * 8 + e * 2 + 0] += fmaf(lf.x, 1.f / kSplitScale, hf.x);
+          v[ch * 8 + e * 2 + 1] += fmaf(lf.y, 1.f / kSplitScale, hf.y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 f = lds128(wb + SL::off_res + sw128_off(lane, ch));
+        v[ch * 4 + 0] += __uint_as_float(f.x);
+        v[ch * 4 + 1] += __uint_as_float(f.y);
+        v[ch * 4 + 2] += __uint_as_float(f.z);
+        v[ch * 4 + 3] += __uint_as_float(f.w);
+      }
+    }
+    __syncwarp();  // every lane has its row: the buffer can take the next block
+    if (have_next && lane == 0) request_residual<OUT>(p, maps, wb + SL::off_res, rbar, tcn, q, cn);
+  }
+  // ---- activation (uniform over the block: act_split is a multiple of 32)
+  const int act = c >= p.act_split ? p.act1 : p.act0;
+  if (kSlowAct) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = v[j];
+      if (act == ACT_ELU1) {  // elu(x) + 1, straight-line (exp on the clamped argument, then select)
+        const float ex = expf(fminf(x, 0.f));
+        x = x > 0.f ? x + 1.f : ex;
+      } else if (act == ACT_DIVS) x = __fdiv_rn(x, p.div);
+      else if (act == ACT_RELU) x = fmaxf(x, 0.f);
+      else if (act == ACT_LEAKY) x = fmaxf(x, 0.01f * x);
+      if (!keep || c + j >= p.N) x = 0.f;  // masked rows; pad channels of the planes stay zero
+      v[j] = x;
+    }
+  } else {
+    const bool is_relu = act == ACT_RELU, is_leaky = act == ACT_LEAKY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float r = fmaxf(v[j], 0.f), l = fmaxf(v[j], 0.01f * v[j]);
+      v[j] = is_relu ? r : (is_leaky ? l : v[j]);
+    }
+  }
+  // ---- stage the row and hand the block to the TMA unit.  The previous block's stores must have finished READING
+  // the staging tiles (they had this whole block's math to do so).
+  if (lane == 0) bulk_wait_read0();
+  __syncwarp();
+  if (OUT & OUT_F32) {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+      sts128(wb + SL::off_f32 + sw128_off(lane, ch),
+             make_uint4(__float_as_uint(v[ch * 4]), __float_as_uint(v[ch * 4 + 1]), __float_as_uint(v[ch * 4 + 2]),
+                        __float_as_uint(v[ch * 4 + 3])));
+  }
+  if (OUT & OUT_PLANES) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x0 = v[ch * 8 + e * 2], x1 = v[ch * 8 + e * 2 + 1];
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn((x0 - hf.x) * kSplitScale, (x1 - hf.y) * kSplitScale);
+        hw[e] = *reinterpret_cast<const uint32_t*>(&h);
+        lw[e] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      sts128(wb + SL::off_pl + sw64_off(lane, ch), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+      sts128(wb + SL::off_pl + STG_BLOCK / 2 + sw64_off(lane, ch), make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    }
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (p.mode == 0) {
+      const int r0 = tc.m_tile * BM + q * 32;
+      if (OUT & OUT_F32) tma_store_3d(&maps.o_f32, wb + SL::off_f32, c, r0, 0);
+      if (OUT & OUT_PLANES) {
+        tma_store_3d(&maps.o_hi, wb + SL::off_pl, c, r0, 0);
+        tma_store_3d(&maps.o_lo, wb + SL::off_pl + STG_BLOCK / 2, c, r0, 0);
+      }
+    } else {
+      const int oh = tc.oh0 + q * 2;
+      if (OUT & OUT_F32) tma_store_4d(&maps.o_f32, wb + SL::off_f32, c, tc.ow0, oh, tc.img);
+      if (OUT & OUT_PLANES) {
+        tma_store_4d(&maps.o_hi, wb + SL::off_pl, c, tc.ow0, oh, tc.img);
+        tma_store_4d(&maps.o_lo, wb + SL::off_pl + STG_BLOCK / 2, c, tc.ow0, oh, tc.img);
+      }
+    }
+    bulk_commit();
+  }
+}
+
 // ---- per-group (32 rows x 32 columns per warp) bodies of the coarse-matching epilogues.  `tb` is the warp's
 // padded smem tile holding the raw accumulators row-per-lane: tb[lane * 33 + j] = 2^8 * <f0[row], f1[col j]>.
 __device__ __forceinline__ void corr_stats_group(const KParams& p, float* tb, int lane, int q, int img, int m_tile, int cbase,
@@ -615,7 +817,7 @@ __device__ __forceinline__ void corr_conf_group(const KParams& p, const float* t
   }
 }
 
-template <int EPI, int OUT, bool kSlowAct, bool kLN>
+template <int EPI, int OUT, bool kSlowAct, bool kLN, bool kTma>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ TMaps maps, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -624,7 +826,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   const uint32_t bars = base + p.stages * p.stage_bytes;        // barrier block
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + p.stages * p.stage_bytes + 256);
   float* tbuf = reinterpret_cast<float*>(gen + p.stages * p.stage_bytes + 512);  // [NUM_EPI_WARPS][32][TBP] transpose tiles
-  float* lnstat = tbuf + NUM_EPI_WARPS * 32 * TBP;                                // [2][4 quadrants][2 halves][32 rows]
+  // [2][4 quadrants][2 halves][32 rows]; the TMA epilogue has no transpose tiles, its staging tiles start at p.stg_off
+  float* lnstat = kTma ? tbuf : tbuf + NUM_EPI_WARPS * 32 * TBP;
   // OUT_RES_PLANES: per epilogue warp one 4 KB buffer ([plane hi|lo][32 rows][32 halves]) for the residual block of the
   // next 32-column group, filled with cp.async one group ahead (the identity loads were latency-bound)
   uint8_t* resbuf = reinterpret_cast<uint8_t*>(lnstat + 2 * NUM_EPI_WARPS * 32);
@@ -632,6 +835,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
   auto tfull_bar = [&](int b) { return bars + 128u + 8u * b; };   // up to 4 accumulator buffers
   auto tempty_bar = [&](int b) { return bars + 160u + 8u * b; };
+  auto res_bar = [&](int w) { return bars + 192u + 8u * w; };     // TMA epilogue: residual block landed (per epilogue warp)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (p.cluster == 2) ? cluster_ctarank() : 0u;
@@ -652,6 +856,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         mbar_init(tfull_bar(b), 1);
         mbar_init(tempty_bar(b), NUM_EPI_WARPS);
       }
+      for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -676,7 +881,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       for (int it = tile_first(p); it < tile_count(p); it += tile_step(p)) {
         const TileCoord tc = decode_tile(p, tile_linear(p, it, cta_rank));
         const int n0 = tc.n_tile * p.bn;
-        if ((OUT & OUT_RES_PLANES) && p.res_stage && p.mode == 0) {
+        if (!kTma && (OUT & OUT_RES_PLANES) && p.res_stage && p.mode == 0) {
           // identity block of the NEXT tile (and of the very first one) -> L2, a whole tile ahead of its consumer: the
           // epilogue's cp.async staging then only sees L2 latency (DRAM latency under this read+write load is ~3 us)
           const int itn = it + tile_step(p);
@@ -808,6 +1013,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     const int half = (warp - 4) >> 2;     // which alternate 32-column groups this warp owns
     const int r_in_tile = q * 32 + lane;  // accumulator row owned by this thread
     uint32_t cc = 0;
+    // TMA epilogue state: staging tiles of this warp, blocks it owns per tile, residual pipeline
+    const uint32_t wb = base + (uint32_t)p.stg_off + (uint32_t)(warp - 4) * (uint32_t)StageLayout<OUT>::bytes;
+    const int ng = (p.bn - half * 32 + 63) / 64;
+    const bool has_res = (OUT & OUT_RES_PLANES) || ((OUT & OUT_RESIDUAL) && p.residual != nullptr);
+    uint32_t rphase = 0;
+    if (kTma && EPI == EPI_STORE && StageLayout<OUT>::kRes && has_res && ng > 0 && lane == 0 && tile_first(p) < tile_count(p)) {
+      const TileCoord t0 = decode_tile(p, tile_linear(p, tile_first(p), cta_rank));
+      request_residual<OUT>(p, maps, wb, res_bar(warp - 4), t0, q, t0.n_tile * p.bn + half * 32);
+    }
     for (int it = tile_first(p); it < tile_count(p); it += tile_step(p)) {
       const int t = tile_linear(p, it, cta_rank);
       const TileCoord tc = decode_tile(p, t);
@@ -823,10 +1037,69 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         row_ok = oh < p.OH && ow < p.OW && tc.img < p.n_imgs;
         row = ((long long)tc.img * p.OH + oh) * p.OW + ow;
       }
-      if (EPI == EPI_STORE && (((OUT & OUT_RESIDUAL) && p.residual) || ((OUT & OUT_RES_PLANES) && !p.res_stage))) {
+      if (!kTma && EPI == EPI_STORE && (((OUT & OUT_RESIDUAL) && p.residual) || ((OUT & OUT_RES_PLANES) && !p.res_stage))) {
         if (it == tile_first(p)) prefetch_residual(p, tc, lane, q, half);  // first tile: no lead time available
         const int itn = it + tile_step(p);
         if (itn < tile_count(p)) prefetch_residual(p, decode_tile(p, tile_linear(p, itn, cta_rank)), lane, q, half);
+      }
+
+      // the residual block to request once block gi of this tile has been consumed: the next block of the tile, else
+      // block 0 of this CTA's next tile
+      auto next_block = [&](int gi, bool& have_next, TileCoord& tcn, int& cn) {
+        have_next = false;
+        tcn = tc;
+        cn = 0;
+        if (!(StageLayout<OUT>::kRes && has_res)) return;
+        if (gi + 1 < ng) {
+          have_next = true;
+          cn = n0 + ((gi + 1) * 2 + half) * 32;
+        } else {
+          const int itn = it + tile_step(p);
+          if (itn < tile_count(p)) {
+            have_next = true;
+            tcn = decode_tile(p, tile_linear(p, itn, cta_rank));
+            cn = tcn.n_tile * p.bn + half * 32;
+          }
+        }
+      };
+      if constexpr (kTma && EPI == EPI_STORE && !kLN) {
+        if (p.num_chunks == 1) {
+          // ---- single-chunk tiles (K <= 128): stream the accumulator block by block straight from TMEM through the
+          // store epilogue (32 live accumulator registers instead of 128); the TMEM buffer is released after the last block
+          const bool keep = !kSlowAct || p.row_mask == nullptr || (row_ok && p.row_mask[row] != 0);
+          const int buf = cc & ((1u << p.nbuf_log2) - 1u);
+          mbar_wait(tfull_bar(buf), (cc >> p.nbuf_log2) & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * p.acc_cols;
+#pragma unroll 1
+          for (int gi = 0; gi < ng; ++gi) {
+            const int c0 = (gi * 2 + half) * 32;
+            uint32_t raw32[32];
+            tmem_ld32(taddr + c0, raw32);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw32[j]);
+            if (gi + 1 == ng) {  // last TMEM read of this warp: hand the buffer back before the block's epilogue
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty_bar(buf));
+            }
+            bool have_next;
+            TileCoord tcn;
+            int cn;
+            next_block(gi, have_next, tcn, cn);
+            finish_block<OUT, kSlowAct>(p, maps, v, wb, res_bar(warp - 4), rphase, has_res, lane, q, tc, n0 + c0, keep,
+                                        have_next, tcn, cn);
+          }
+          if (ng == 0) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+          }
+          ++cc;
+          continue;
+        }
       }
 
       // ---- drain the chunk accumulators into fp32 registers (round-to-nearest adds)
@@ -930,37 +1203,60 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[gi][j] = (acc[gi][j] - mean) * rstd;
       }
-      const bool staged = (OUT & OUT_RES_PLANES) && p.res_stage;
-      uint8_t* rb = resbuf + (warp - 4) * RES_BUF_BYTES;
-      if (staged) issue_residual_block(p, tc, lane, q, n0 + half * 32, rb);  // group 0 of this warp
+      if constexpr (kTma) {
+        const bool keep = !kSlowAct || p.row_mask == nullptr || (row_ok && p.row_mask[row] != 0);
 #pragma unroll 1
-      for (int gi = 0; gi < 4; ++gi) {
-        const int c0 = (gi * 2 + half) * 32;
-        if (c0 >= p.bn) break;  // warp-uniform
-        uint2 rh[8], rl[8];
+        for (int gi = 0; gi < ng; ++gi) {  // rolled: one copy of the block epilogue (instruction cache)
+          float v[32];
+#define GIMB_TAKE(G) _Pragma("unroll") for (int j = 0; j < 32; ++j) v[j] = acc[G][j];
+          switch (gi) {  // static register indices for every case
+            case 0: GIMB_TAKE(0) break;
+            case 1: GIMB_TAKE(1) break;
+            case 2: GIMB_TAKE(2) break;
+            default: GIMB_TAKE(3) break;
+          }
+#undef GIMB_TAKE
+          bool have_next;
+          TileCoord tcn;
+          int cn;
+          next_block(gi, have_next, tcn, cn);
+          finish_block<OUT, kSlowAct>(p, maps, v, wb, res_bar(warp - 4), rphase, has_res, lane, q, tc,
+                                      n0 + (gi * 2 + half) * 32, keep, have_next, tcn, cn);
+        }
+      } else {
+      const bool staged = (OUT & OUT_RES_PLANES) && p.res_stage;
+        uint8_t* rb = resbuf + (warp - 4) * RES_BUF_BYTES;
+        if (staged) issue_residual_block(p, tc, lane, q, n0 + half * 32, rb);  // group 0 of this warp
+#pragma unroll 1
+        for (int gi = 0; gi < 4; ++gi) {
+          const int c0 = (gi * 2 + half) * 32;
+          if (c0 >= p.bn) break;  // warp-uniform
+          uint2 rh[8], rl[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) { rh[it] = make_uint2(0u, 0u); rl[it] = make_uint2(0u, 0u); }
-        if (staged) {
-          // the residual block of this group was requested a whole group (or the drain) ago: pull it into registers,
-          // then reuse the buffer for the next group's request
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          __syncwarp();
-          const int rsub = lane >> 3, cq = lane & 7;
+          for (int it = 0; it < 8; ++it) { rh[it] = make_uint2(0u, 0u); rl[it] = make_uint2(0u, 0u); }
+          if (staged) {
+            // the residual block of this group was requested a whole group (or the drain) ago: pull it into registers,
+            // then reuse the buffer for the next group's request
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const int rsub = lane >> 3, cq = lane & 7;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            rh[it] = *reinterpret_cast<const uint2*>(rb + (it * 4 + rsub) * 64 + cq * 8);
-            rl[it] = *reinterpret_cast<const uint2*>(rb + 2048 + (it * 4 + rsub) * 64 + cq * 8);
+            for (int it = 0; it < 8; ++it) {
+              rh[it] = *reinterpret_cast<const uint2*>(rb + (it * 4 + rsub) * 64 + cq * 8);
+              rl[it] = *reinterpret_cast<const uint2*>(rb + 2048 + (it * 4 + rsub) * 64 + cq * 8);
+            }
+            __syncwarp();
+            const int c1 = ((gi + 1) * 2 + half) * 32;
+            if (gi + 1 < 4 && c1 < p.bn) issue_residual_block(p, tc, lane, q, n0 + c1, rb);
           }
           __syncwarp();
-          const int c1 = ((gi + 1) * 2 + half) * 32;
-          if (gi + 1 < 4 && c1 < p.bn) issue_residual_block(p, tc, lane, q, n0 + c1, rb);
+          stage_group(tb, lane, acc, gi);
+          __syncwarp();
+          store_group<OUT, kSlowAct>(p, tb, lane, q, tc, n0 + c0, rh, rl, staged);
         }
-        __syncwarp();
-        stage_group(tb, lane, acc, gi);
-        __syncwarp();
-        store_group<OUT, kSlowAct>(p, tb, lane, q, tc, n0 + c0, rh, rl, staged);
       }
     }
+    if (kTma && EPI == EPI_STORE && lane == 0) bulk_wait0();  // all bulk stores of this warp are complete
   }
 
   // ---- teardown (cluster mode: no CTA may exit while its peer can still multicast into it / arrive on its barriers)
@@ -1009,7 +1305,7 @@ int get_encode(EncodeTiledFn* out) {
 // fp16 tensor map, SWIZZLE_64B, inner box = 32 elements (64 B).  dims/strides innermost first; strides in BYTES for
 // dims 1.. (rank-1 entries).
 int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box) {
+             const uint32_t* box, bool f32 = false) {
   EncodeTiledFn enc;
   GIMB_TRY(get_encode(&enc));
   cuuint64_t gd[5];
@@ -1019,8 +1315,10 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, co
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   GIMB_CHECK(((uintptr_t)ptr & 15) == 0, "tensor map: base address not 16-byte aligned");
   for (int i = 0; i + 1 < rank; ++i) GIMB_CHECK(gs[i] % 16 == 0, "tensor map: stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  // fp16 planes: 32-channel (64-byte) box rows, SWIZZLE_64B; fp32 tensors: 32-channel (128-byte) rows, SWIZZLE_128B
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                   const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GIMB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rank %d, dims %llu %llu %llu)", (int)r, rank,
              (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)(rank > 2 ? gd[2] : 0));
@@ -1046,6 +1344,34 @@ int chunk_kb_setting() {
     if (v < 1) v = CHUNK_KB_DEFAULT;
   }
   return v;
+}
+
+// store epilogue: bulk tensor stores / loads (default) or the LSU path (GIMB_EPI=legacy)
+bool tma_epilogue_setting() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GIMB_EPI");
+    v = (e && strcmp(e, "legacy") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Tensor map whose box is one epilogue-warp block: 32 channels x 32 rows (row mode) or 32 channels x 16 x 2 pixels
+// (conv mode: the two image rows of the 8 x 16 patch that belong to one TMEM lane quadrant).  `width` channels are
+// addressable (pitch `ld` elements); everything outside is clipped on stores and zero-filled on loads.
+int block_map(CUtensorMap* m, const void* ptr, bool f32, int mode, uint64_t width, uint64_t ld, uint64_t M, int B, int OH,
+              int OW) {
+  const uint64_t es = f32 ? 4 : 2;
+  if (mode == 0) {
+    uint64_t dims[3] = {width, M, 1};
+    uint64_t strides[2] = {ld * es, M * ld * es};
+    uint32_t box[3] = {32, 32, 1};
+    return make_map(m, ptr, 3, dims, strides, box, f32);
+  }
+  uint64_t dims[4] = {width, (uint64_t)OW, (uint64_t)OH, (uint64_t)B};
+  uint64_t strides[3] = {ld * es, (uint64_t)OW * ld * es, (uint64_t)OH * OW * ld * es};
+  uint32_t box[4] = {32, TW, 2, 1};
+  return make_map(m, ptr, 4, dims, strides, box, f32);
 }
 
 int rows_map(CUtensorMap* m, const __half* ptr, uint64_t K, uint64_t rows, uint64_t ld, uint32_t box_rows,
@@ -1137,20 +1463,48 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn));
   }
   p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * BK * 2;
-  // the planes-residual epilogue stages the identity block through smem (8 warps x 4 KB) when the ring still
-  // keeps >= 3 stages (or the whole K + 1) beside it
-  const int res_bytes = NUM_EPI_WARPS * 4096;
+  const bool tma_epi = tma_epilogue_setting();
+  const bool want_f32 = g.out_f32 != nullptr, want_planes = g.out.hi != nullptr;
+  const bool any_res = g.residual != nullptr || g.residual_planes.hi != nullptr;
+  int extra;  // shared memory beside the operand ring
+  int wbytes = 0;  // TMA epilogue: staging bytes per epilogue warp (must match StageLayout<OUT> of the launched variant)
   p.res_stage = 0;
-  if (g.residual_planes.hi) {
-    const int st = (SMEM_LIMIT - SMEM_EXTRA - res_bytes) / p.stage_bytes;
-    if (st >= std::min(3, p.num_kb + 1)) p.res_stage = 1;
+  if (tma_epi) {
+    // [ring][barriers 512][LayerNorm exchange 2048][pad 512][8 warps x staging tiles (4 KB per staged tensor)]
+    GIMB_CHECK(g.act_split % 32 == 0, "umma_gemm: act_split must be a multiple of 32");
+    // the kernel variants with a residual slot reserve it even when no residual is given
+    const bool res_slot = any_res || (want_f32 && want_planes);
+    wbytes = STG_BLOCK * ((res_slot ? 1 : 0) + (want_f32 ? 1 : 0) + (want_planes ? 1 : 0));
+    extra = 1024 + 3072 + NUM_EPI_WARPS * wbytes;
+    const uint64_t Mrows = (uint64_t)(g.mode == 0 ? g.M : (int64_t)g.B * g.OH * g.OW);
+    if (want_f32) GIMB_TRY(block_map(&maps.o_f32, g.out_f32, true, g.mode, g.N, g.N, Mrows, g.B, g.OH, g.OW));
+    if (want_planes) {
+      GIMB_TRY(block_map(&maps.o_hi, g.out.hi, false, g.mode, g.out.ld, g.out.ld, Mrows, g.B, g.OH, g.OW));
+      GIMB_TRY(block_map(&maps.o_lo, g.out.lo, false, g.mode, g.out.ld, g.out.ld, Mrows, g.B, g.OH, g.OW));
+    }
+    if (g.residual) GIMB_TRY(block_map(&maps.r_f32, g.residual, true, g.mode, g.N, g.N, Mrows, g.B, g.OH, g.OW));
+    if (g.residual_planes.hi) {
+      const uint64_t ldr = g.residual_planes.ld;
+      GIMB_TRY(block_map(&maps.r_hi, g.residual_planes.hi, false, g.mode, ldr, ldr, Mrows, g.B, g.OH, g.OW));
+      GIMB_TRY(block_map(&maps.r_lo, g.residual_planes.lo, false, g.mode, ldr, ldr, Mrows, g.B, g.OH, g.OW));
+    }
+  } else {
+    // legacy: the planes-residual epilogue stages the identity block through smem (8 warps x 4 KB) when the ring still
+    // keeps >= 3 stages (or the whole K + 1) beside it
+    const int res_bytes = NUM_EPI_WARPS * 4096;
+    if (g.residual_planes.hi) {
+      const int st = (SMEM_LIMIT - SMEM_EXTRA - res_bytes) / p.stage_bytes;
+      if (st >= std::min(3, p.num_kb + 1)) p.res_stage = 1;
+    }
+    if (p.res_stage && g.mode == 0) {
+      GIMB_TRY(rows_map(&maps.r_hi, g.residual_planes.hi, g.N, g.M, g.residual_planes.ld, BM));
+      GIMB_TRY(rows_map(&maps.r_lo, g.residual_planes.lo, g.N, g.M, g.residual_planes.ld, BM));
+    }
+    extra = SMEM_EXTRA + (p.res_stage ? res_bytes : 0);
   }
-  if (p.res_stage && g.mode == 0) {
-    GIMB_TRY(rows_map(&maps.r_hi, g.residual_planes.hi, g.N, g.M, g.residual_planes.ld, BM));
-    GIMB_TRY(rows_map(&maps.r_lo, g.residual_planes.lo, g.N, g.M, g.residual_planes.ld, BM));
-  }
-  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - SMEM_EXTRA - (p.res_stage ? res_bytes : 0)) / p.stage_bytes);
+  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - extra) / p.stage_bytes);
   p.stages = std::max(2, std::min(p.stages, std::max(3, p.num_kb + 1)));
+  p.stg_off = p.stages * p.stage_bytes + 3072;
   p.num_tiles = m_tiles * p.n_tiles;
   // K <= 128: one in-TMEM chunk (24 accumulation steps keep the truncation bias at the fp32-FFMA level and save a
   // drain hand-shake per tile); longer K: chunks of CHUNK_KB k-blocks
@@ -1178,7 +1532,8 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     GIMB_TRY(rows_map(&maps.bh_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn / 2));
     GIMB_TRY(rows_map(&maps.bh_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn / 2));
   }
-  const int smem = p.stages * p.stage_bytes + SMEM_EXTRA + (p.res_stage ? res_bytes : 0);
+  const int smem = p.stages * p.stage_bytes + extra;
+  GIMB_CHECK(smem <= SMEM_LIMIT, "umma_gemm: shared memory plan %d B exceeds the limit", smem);
   const bool slow = g.act0 >= ACT_ELU1 || g.act1 >= ACT_ELU1 || g.row_mask != nullptr;
   const bool f32 = g.out_f32 != nullptr, planes = g.out.hi != nullptr, res = g.residual != nullptr;
   const bool resp = g.residual_planes.hi != nullptr;
@@ -1194,15 +1549,26 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   lattr[0].id = cudaLaunchAttributeClusterDimension;
   lattr[0].val.clusterDim.x = p.cluster; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
   lcfg.attrs = lattr; lcfg.numAttrs = 1;
-#define GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, LNV)                                                                   \
+#define GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, TMAV)                                                              \
   do {                                                                                                            \
     static bool done = false;                                                                                     \
     if (!done) {                                                                                                  \
-      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV>,                                  \
+      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, TMAV>,                            \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);                      \
       done = true;                                                                                                \
     }                                                                                                             \
-    if (aerr == cudaSuccess) aerr = cudaLaunchKernelEx(&lcfg, umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV>, maps, p); \
+    if (TMAV && StageLayout<OUTV>::bytes != wbytes) {                                                             \
+      set_error("umma_gemm: staging plan (%d B) does not match the kernel variant (%d B)", wbytes,                \
+                (int)StageLayout<OUTV>::bytes);                                                                   \
+      return 1;                                                                                                   \
+    }                                                                                                             \
+    if (aerr == cudaSuccess)                                                                                      \
+      aerr = cudaLaunchKernelEx(&lcfg, umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, TMAV>, maps, p);             \
+  } while (0)
+#define GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, LNV)                    \
+  do {                                                              \
+    if (tma_epi) GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, true);     \
+    else GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, false);            \
   } while (0)
 #define GIMB_LAUNCH_VARIANT(OUTV, SLOWV) GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, false)
   if (g.layernorm) {
@@ -1230,6 +1596,7 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   }
 #undef GIMB_LAUNCH_VARIANT
 #undef GIMB_LAUNCH_VARIANT_LN
+#undef GIMB_LAUNCH_VARIANT_T
   GIMB_CUDA(aerr);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
@@ -1297,15 +1664,15 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
   static bool attr_done = false;
   if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = std::min(p.num_tiles, ctx.sm_count);
   if (pass == 0)
-    umma_gemm_kernel<EPI_CORR_STATS, 0, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   else
-    umma_gemm_kernel<EPI_CORR_CONF, 0, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;
