@@ -44,6 +44,7 @@ EXPORTS = {
     "gimb_loftr_set_engine": (c_int, [c_void_p, c_int]),
     "gimb_loftr_last_profile": (c_int, [c_void_p, POINTER(c_char_p), POINTER(c_float), POINTER(c_int)]),
     "gimb_bench_layer": (c_int, [c_int] * 11 + [POINTER(c_float), c_void_p]),
+    "gimb_probe_tma": (c_int, [c_int, c_int, POINTER(c_float), c_void_p]),
     "gimb_test_conv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_void_p]),

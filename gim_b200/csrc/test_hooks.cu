@@ -155,3 +155,13 @@ extern "C" int gimb_bench_layer(int B, int H, int W, int C1, int C2, int Cout, i
   for (void* p : bufs) cudaFree(p);
   return rc;
 }
+
+extern "C" int gimb_probe_tma(int variant, int iters, float* gbps_out, void* stream) {
+  GIMB_CHECK(gbps_out, "gimb_probe_tma: null argument");
+  Ctx ctx;
+  ctx.stream = (cudaStream_t)stream;
+  int dev = 0;
+  GIMB_CUDA(cudaGetDevice(&dev));
+  GIMB_CUDA(cudaDeviceGetAttribute(&ctx.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  return tma_probe(ctx, variant, iters, gbps_out);
+}

@@ -648,24 +648,42 @@ __device__ __forceinline__ void finish_block(const KParams& p, const TMaps& maps
   // ---- activation (uniform over the block: act_split is a multiple of 32)
   const int act = c >= p.act_split ? p.act1 : p.act0;
   if (kSlowAct) {
+    if (act == ACT_ELU1) {
+      // elu(x) + 1 = x + 1 (x > 0), exp(x) (x <= 0).  exp through one MUFU.EX2 on x * log2(e): for x <= 0 the absolute
+      // error is <= |x| e^x * 1.44 * 2^-24 + 2 ulp(e^x) < 4e-8 - below half an ulp of the values near 1 it is added to
+      // downstream (expf's range reduction cost ~3x the instructions of the whole block epilogue).
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = v[j];
-      if (act == ACT_ELU1) {  // elu(x) + 1, straight-line (exp on the clamped argument, then select)
-        const float ex = expf(fminf(x, 0.f));
-        x = x > 0.f ? x + 1.f : ex;
-      } else if (act == ACT_DIVS) x = __fdiv_rn(x, p.div);
-      else if (act == ACT_RELU) x = fmaxf(x, 0.f);
-      else if (act == ACT_LEAKY) x = fmaxf(x, 0.01f * x);
-      if (!keep || c + j >= p.N) x = 0.f;  // masked rows; pad channels of the planes stay zero
-      v[j] = x;
+      for (int j = 0; j < 32; ++j) {
+        float ex;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fminf(v[j], 0.f) * 1.4426950408889634f));
+        v[j] = v[j] > 0.f ? v[j] + 1.f : ex;
+      }
+    } else if (act == ACT_DIVS) {
+      // x / div, correctly rounded: q = x * r with r = RN(1 / div), one residual correction (Markstein); the operands
+      // here are O(1) activations and a token count, far from the under/overflow cases the library division guards
+      const float d = p.div, r = __frcp_rn(d);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float q0 = v[j] * r;
+        v[j] = fmaf(fmaf(-q0, d, v[j]), r, q0);
+      }
+    } else if (act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == ACT_LEAKY) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
     }
-  } else {
-    const bool is_relu = act == ACT_RELU, is_leaky = act == ACT_LEAKY;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float r = fmaxf(v[j], 0.f), l = fmaxf(v[j], 0.01f * v[j]);
-      v[j] = is_relu ? r : (is_leaky ? l : v[j]);
+    for (int j = 0; j < 32; ++j)
+      if (!keep || c + j >= p.N) v[j] = 0.f;  // masked rows; pad channels of the planes stay zero
+  } else {
+    if (act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == ACT_LEAKY) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
     }
   }
   // ---- stage the row and hand the block to the TMA unit.  The previous block's stores must have finished READING
@@ -1600,6 +1618,96 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   GIMB_CUDA(aerr);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------- TMA load-rate probe
+// Measurement helper (tools/probe_tma.py): every CTA (one per SM, one thread) streams boxes from an L2-resident
+// tensor through a 4-stage ring.  Answers one design question: what does the L2 -> SM path deliver for 64-byte box
+// rows (BK = 32 fp16, SWIZZLE_64B - what the GEMM uses) against 128-byte rows (BK = 64, SWIZZLE_128B)?
+namespace {
+__global__ void __launch_bounds__(32, 1) tma_probe_kernel(const __grid_constant__ CUtensorMap map, int variant, int box_bytes,
+                                                          int boxes, int iters, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + 4 * 49152;
+  if (threadIdx.x != 0) return;
+  for (int s = 0; s < 4; ++s) mbar_init(bars + 8 * s, 1);
+  fence_barrier_init();
+  const int stage_bytes = box_bytes * boxes;
+  auto issue = [&](int i) {
+    const int s = i & 3;
+    const uint32_t dst = base + s * 49152, bar = bars + 8 * s;
+    mbar_expect_tx(bar, (uint32_t)stage_bytes);
+    const int t = (int)(((long long)blockIdx.x * 7919 + (long long)i * gridDim.x) % n_tiles);
+    for (int b = 0; b < boxes; ++b) {
+      if (variant < 2) {  // row mode: tensor [rows][256 ch]; boxes walk the k-blocks of a 128-row tile
+        const int bk = variant == 0 ? 32 : 64;
+        const int kb = (i * boxes + b) % (256 / bk);
+        tma_load_3d(dst + b * box_bytes, &map, bar, kb * bk, t * 128, 0);
+      } else {           // conv mode: tensor [4][240][320][64 ch]; boxes are taps of an 8 x 16 patch
+        const int bk = variant == 2 ? 32 : 64;
+        const int img = t / 600, r = t % 600, th = r / 20, tw = r % 20;
+        const int tap = (i * boxes + b) % (9 * (64 / bk));
+        const int cb = tap % (64 / bk), kk = tap / (64 / bk);
+        tma_load_4d(dst + b * box_bytes, &map, bar, cb * bk, tw * 16 + kk % 3 - 1, th * 8 + kk / 3 - 1, img);
+      }
+    }
+  };
+  for (int i = 0; i < 4 && i < iters; ++i) issue(i);
+  for (int i = 0; i < iters; ++i) {
+    mbar_wait(bars + 8 * (i & 3), (i >> 2) & 1);
+    if (i + 4 < iters) issue(i + 4);
+  }
+}
+}  // namespace
+
+int tma_probe(Ctx& ctx, int variant, int iters, float* gbps) {
+  GIMB_CHECK(variant >= 0 && variant < 4 && iters > 0, "tma_probe: bad arguments");
+  const bool conv = variant >= 2, wide = variant & 1;
+  const size_t elems = conv ? (size_t)4 * 240 * 320 * 64 : (size_t)65536 * 256;
+  __half* buf = nullptr;
+  GIMB_CUDA(cudaMalloc(&buf, elems * 2));
+  GIMB_CUDA(cudaMemsetAsync(buf, 0, elems * 2, ctx.stream));
+  EncodeTiledFn enc;
+  GIMB_TRY(get_encode(&enc));
+  CUtensorMap map;
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  int rank, n_tiles;
+  const cuuint32_t bk = wide ? 64 : 32;
+  if (!conv) {
+    rank = 3; n_tiles = 65536 / 128;
+    gd[0] = 256; gd[1] = 65536; gd[2] = 1; gs[0] = 512; gs[1] = 512ull * 65536;
+    bx[0] = bk; bx[1] = 128; bx[2] = 1;
+  } else {
+    rank = 4; n_tiles = 4 * 600;
+    gd[0] = 64; gd[1] = 320; gd[2] = 240; gd[3] = 4; gs[0] = 128; gs[1] = 128ull * 320; gs[2] = 128ull * 320 * 240;
+    bx[0] = bk; bx[1] = 16; bx[2] = 8; bx[3] = 1;
+  }
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, buf, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GIMB_CHECK(r == CUDA_SUCCESS, "tma_probe: cuTensorMapEncodeTiled failed with %d", (int)r);
+  const int box_bytes = (int)bk * 2 * 128, boxes = wide ? 2 : 4;  // 32 KB per ring stage either way
+  const int smem = 4 * 49152 + 1024 + 64;
+  GIMB_CUDA(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t e0, e1;
+  GIMB_CUDA(cudaEventCreate(&e0));
+  GIMB_CUDA(cudaEventCreate(&e1));
+  tma_probe_kernel<<<ctx.sm_count, 32, smem, ctx.stream>>>(map, variant, box_bytes, boxes, iters, n_tiles);  // warm L2
+  GIMB_CUDA(cudaEventRecord(e0, ctx.stream));
+  tma_probe_kernel<<<ctx.sm_count, 32, smem, ctx.stream>>>(map, variant, box_bytes, boxes, iters, n_tiles);
+  GIMB_CUDA(cudaEventRecord(e1, ctx.stream));
+  GIMB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  GIMB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *gbps = (float)((double)ctx.sm_count * iters * box_bytes * boxes / (ms * 1e-3) / 1e9);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
   return 0;
 }
 

@@ -76,4 +76,7 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass);
 // fp32 -> split planes (weights at load time; test helper)
 int split_planes(Ctx& ctx, const float* src, int64_t rows, int cols, int src_ld, const SplitPlanes& dst);
 
+// measurement helper: aggregate L2 -> SM TMA load rate (GB/s); variant 0/1 = row boxes of 64/128-byte rows, 2/3 = conv boxes
+int tma_probe(Ctx& ctx, int variant, int iters, float* gbps);
+
 }  // namespace gimb

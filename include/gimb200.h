@@ -167,6 +167,10 @@ int gimb_test_conv(const float* in, const float* in2, int B, int H, int W, int C
 int gimb_bench_layer(int B, int H, int W, int C1, int C2, int Cout, int ksize, int stride, int flags, int act,
                      int iters, float* ms_out, void* stream);
 
+/* Measurement helper (tools/probe_tma.py): aggregate L2 -> SM bulk-tensor load rate in GB/s for boxes with 64-byte
+ * rows (variant 0: row mode, 2: conv patches) or 128-byte rows (1, 3). */
+int gimb_probe_tma(int variant, int iters, float* gbps_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
