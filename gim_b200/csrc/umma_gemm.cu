@@ -60,6 +60,7 @@ struct KParams {
   int KH, KW, stride, pad;
   int cb1, cb2, K1;  // k-blocks of a / a2 per tap; channels of a
   int ldk;
+  int bk;            // K extent of one stage: 32 (64-byte tile rows, SWIZZLE_64B) or 64 (128-byte rows, SWIZZLE_128B)
   int N, n_tiles, bn;
   int stages, stage_bytes;
   int num_tiles, num_kb, num_chunks, chunk_kb;
@@ -199,6 +200,17 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
   d |= (uint64_t)4 << 61;          // SWIZZLE_64B
   return d;
 }
+// same for tiles with 128-byte rows (BK = 64): SWIZZLE_128B (layout type 2), 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool wide) { return wide ? make_desc_sw128(saddr) : make_desc_sw64(saddr); }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -888,7 +900,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t b_plane = (uint32_t)p.bn * (BK * 2);  // bytes of one B plane tile
+  const uint32_t a_plane = (uint32_t)BM * (uint32_t)p.bk * 2u;    // bytes of one A plane tile
+  const uint32_t b_plane = (uint32_t)p.bn * (uint32_t)p.bk * 2u;  // bytes of one B plane tile
+  const bool wide = p.bk == 64;
 
   if (warp == 0) {
     // =============================================================== TMA producer
@@ -916,21 +930,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sA = base + stage * p.stage_bytes;
-          const uint32_t sB = sA + 2 * A_TILE_BYTES;
+          const uint32_t sB = sA + 2 * a_plane;
           const uint32_t fb = full_bar(stage);
           mbar_expect_tx(fb, (uint32_t)p.stage_bytes);
           int bk;  // k coordinate into the weight planes
           if (p.mode == 0) {
             const int m0 = tc.m_tile * BM;
             if (kb < p.cb1) {
-              bk = kb * BK;
-              tma_load_3d(sA, &maps.a_hi[0], fb, kb * BK, m0, tc.img);
-              tma_load_3d(sA + A_TILE_BYTES, &maps.a_lo[0], fb, kb * BK, m0, tc.img);
+              bk = kb * p.bk;
+              tma_load_3d(sA, &maps.a_hi[0], fb, kb * p.bk, m0, tc.img);
+              tma_load_3d(sA + a_plane, &maps.a_lo[0], fb, kb * p.bk, m0, tc.img);
             } else {
-              const int k2 = (kb - p.cb1) * BK;
+              const int k2 = (kb - p.cb1) * p.bk;
               bk = p.K1 + k2;
               tma_load_3d(sA, &maps.a2_hi, fb, k2, m0, 0);
-              tma_load_3d(sA + A_TILE_BYTES, &maps.a2_lo, fb, k2, m0, 0);
+              tma_load_3d(sA + a_plane, &maps.a2_lo, fb, k2, m0, 0);
             }
           } else {
             const int tap = kb / p.cb1, cb = kb - tap * p.cb1;
@@ -942,9 +956,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
               dh = (dh - py) / 2;
               dw = (dw - px) / 2;
             }
-            bk = tap * p.ldk + cb * BK;
-            tma_load_4d(sA, &maps.a_hi[view], fb, cb * BK, tc.ow0 + dw, tc.oh0 + dh, tc.img);
-            tma_load_4d(sA + A_TILE_BYTES, &maps.a_lo[view], fb, cb * BK, tc.ow0 + dw, tc.oh0 + dh, tc.img);
+            bk = tap * p.ldk + cb * p.bk;
+            tma_load_4d(sA, &maps.a_hi[view], fb, cb * p.bk, tc.ow0 + dw, tc.oh0 + dh, tc.img);
+            tma_load_4d(sA + a_plane, &maps.a_lo[view], fb, cb * p.bk, tc.ow0 + dw, tc.oh0 + dh, tc.img);
           }
           const int bb = (p.mode == 0) ? tc.img : 0;  // weights: one matrix; coarse matching: f1 of the same pair
           if (p.cluster == 2) {
@@ -968,6 +982,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;  // chunk counter across tiles: TMEM buffer = cc mod (number of buffers)
+      const uint64_t dconst = make_desc(0u, wide);  // descriptor with a zero start address
+      const int nk16 = p.bk >> 4;
       for (int it = tile_first(p); it < tile_count(p); it += tile_step(p)) {
         int kb = 0;
         for (int ch = 0; ch < p.num_chunks; ++ch, ++cc) {
@@ -979,40 +995,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           // pass 1 over the chunk's stages: the two cross terms  D  = sum_k (A_hi*B_lo + A_lo*B_hi)      [lo = 2^8 * residual]
           // pass 2 over the same stages:    the main term        D  = sum_k A_hi*B_hi + 2^-8 * D         (scale-input-d = 8
           // on the first MMA of the pass).  The cross sum is accumulated at its own (small) magnitude and scaled exactly.
+          // One thread issues every MMA of the CTA, so the loop is kept lean: the descriptors of a stage differ only in
+          // the start-address field (bits 0-13, 16-byte units) - one add per operand instead of rebuilding them
+          // (at N = 64 an MMA retires in ~40 cycles; a 30-instruction issue sequence made the issuer the bottleneck).
           int st = stage;
           uint32_t ph = phase;
           bool first = true;
           for (int k2 = kb; k2 < kb_end; ++k2) {
             mbar_wait(full_bar(st), ph);
             tc_fence_after();
-            const uint32_t sA = base + st * p.stage_bytes;
-            const uint32_t sB = sA + 2 * A_TILE_BYTES;
+            const uint64_t dA_hi = dconst + (((base + st * p.stage_bytes) & 0x3FFFFu) >> 4);
+            const uint64_t dA_lo = dA_hi + (a_plane >> 4);
+            const uint64_t dB_hi = dA_hi + (a_plane >> 3);
+            const uint64_t dB_lo = dB_hi + (b_plane >> 4);
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
-              const uint32_t koff = kk * 32;  // 16 fp16 = 32 bytes inside the 64-byte swizzle row
-              const uint64_t a_hi = make_desc_sw64(sA + koff);
-              const uint64_t a_lo = make_desc_sw64(sA + A_TILE_BYTES + koff);
-              const uint64_t b_hi = make_desc_sw64(sB + koff);
-              const uint64_t b_lo = make_desc_sw64(sB + b_plane + koff);
-              umma_f16(tacc, a_hi, b_lo, p.idesc, first ? 0u : 1u);
-              umma_f16(tacc, a_lo, b_hi, p.idesc, 1);
-              first = false;
+            for (int kk = 0; kk < 4; ++kk) {  // 16 fp16 = 32 bytes = 2 address units inside the swizzled tile row
+              if (kk < nk16) {
+                umma_f16(tacc, dA_hi + 2 * kk, dB_lo + 2 * kk, p.idesc, (first && kk == 0) ? 0u : 1u);
+                umma_f16(tacc, dA_lo + 2 * kk, dB_hi + 2 * kk, p.idesc, 1);
+              }
             }
+            first = false;
             if (++st == p.stages) { st = 0; ph ^= 1; }
           }
           first = true;
           for (; kb < kb_end; ++kb) {
-            const uint32_t sA = base + stage * p.stage_bytes;
-            const uint32_t sB = sA + 2 * A_TILE_BYTES;
+            const uint64_t dA_hi = dconst + (((base + stage * p.stage_bytes) & 0x3FFFFu) >> 4);
+            const uint64_t dB_hi = dA_hi + (a_plane >> 3);
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
-              const uint32_t koff = kk * 32;
-              const uint64_t a_hi = make_desc_sw64(sA + koff);
-              const uint64_t b_hi = make_desc_sw64(sB + koff);
-              if (first) umma_f16_scaled8(tacc, a_hi, b_hi, p.idesc);
-              else umma_f16(tacc, a_hi, b_hi, p.idesc, 1);
-              first = false;
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kk < nk16) {
+                if (first && kk == 0) umma_f16_scaled8(tacc, dA_hi, dB_hi, p.idesc);
+                else umma_f16(tacc, dA_hi + 2 * kk, dB_hi + 2 * kk, p.idesc, 1);
+              }
             }
+            first = false;
             // smem stage reusable once every MMA of both passes has read it (in both CTAs of a pair)
             if (p.cluster == 2) umma_commit_mc(empty_bar(stage), (uint16_t)3);
             else umma_commit(empty_bar(stage));
@@ -1333,10 +1350,11 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, co
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   GIMB_CHECK(((uintptr_t)ptr & 15) == 0, "tensor map: base address not 16-byte aligned");
   for (int i = 0; i + 1 < rank; ++i) GIMB_CHECK(gs[i] % 16 == 0, "tensor map: stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
-  // fp16 planes: 32-channel (64-byte) box rows, SWIZZLE_64B; fp32 tensors: 32-channel (128-byte) rows, SWIZZLE_128B
+  // 64-byte box rows (32 fp16): SWIZZLE_64B; 128-byte rows (64 fp16 or 32 fp32): SWIZZLE_128B
   CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
                    const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   (f32 || bx[0] * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GIMB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rank %d, dims %llu %llu %llu)", (int)r, rank,
              (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)(rank > 2 ? gd[2] : 0));
@@ -1374,6 +1392,17 @@ bool tma_epilogue_setting() {
   return v == 1;
 }
 
+// K extent of a ring stage: 0 = choose per layer (default), GIMB_BK=32 / 64 force it where possible
+int bk_setting() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GIMB_BK");
+    v = e ? atoi(e) : 0;
+    if (v != 32 && v != 64) v = 0;
+  }
+  return v;
+}
+
 // Tensor map whose box is one epilogue-warp block: 32 channels x 32 rows (row mode) or 32 channels x 16 x 2 pixels
 // (conv mode: the two image rows of the 8 x 16 patch that belong to one TMEM lane quadrant).  `width` channels are
 // addressable (pitch `ld` elements); everything outside is clipped on stores and zero-filled on loads.
@@ -1393,10 +1422,10 @@ int block_map(CUtensorMap* m, const void* ptr, bool f32, int mode, uint64_t widt
 }
 
 int rows_map(CUtensorMap* m, const __half* ptr, uint64_t K, uint64_t rows, uint64_t ld, uint32_t box_rows,
-             uint64_t nbatch = 1) {
+             uint64_t nbatch = 1, uint32_t bk = BK) {
   uint64_t dims[3] = {K, rows, nbatch};
   uint64_t strides[2] = {ld * 2, rows * ld * 2};
-  uint32_t box[3] = {BK, box_rows, 1};
+  uint32_t box[3] = {bk, box_rows, 1};
   return make_map(m, ptr, 3, dims, strides, box);
 }
 
@@ -1431,27 +1460,55 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   p.bn = cdiv(cdiv(g.N, p.n_tiles), 16) * 16;
   p.KH = g.KH; p.KW = g.KW; p.stride = g.stride; p.pad = g.pad;
   p.K1 = g.K1;
-  p.cb1 = cdiv(g.K1, BK);
-  p.cb2 = 0;
+  // ---- shared-memory plan.  Epilogue staging first (TMA epilogue: 4 KB per staged tensor per epilogue warp), then the
+  // K extent of a ring stage: 64 (128-byte tile rows) when the layer is K-heavy and two such stages fit - the L2 -> SM
+  // path delivers ~1.5x the bytes per clock for 128-byte box rows (tools/probe_tma.py: conv patches 22.6 -> 33.3
+  // B/clk/SM, row tiles 41.9 -> 49.4), and the K-heavy layers are bound by exactly that path.
+  const bool tma_epi = tma_epilogue_setting();
+  const bool want_f32 = g.out_f32 != nullptr, want_planes = g.out.hi != nullptr;
+  const bool any_res = g.residual != nullptr || g.residual_planes.hi != nullptr;
+  int wbytes = 0;  // TMA epilogue: staging bytes per epilogue warp (must match StageLayout<OUT> of the launched variant)
+  if (tma_epi) {
+    // the kernel variants with a residual slot reserve it even when no residual is given
+    const bool res_slot = any_res || (want_f32 && want_planes);
+    wbytes = STG_BLOCK * ((res_slot ? 1 : 0) + (want_f32 ? 1 : 0) + (want_planes ? 1 : 0));
+  }
+  // [alignment slack 1024][ring][barriers 512 | LayerNorm exchange 2048 (fused-LN kernels only) | pad][staging tiles]
+  const int fixed_tma = g.layernorm ? 3072 : 1024;
+  const int extra_tma = 1024 + fixed_tma + NUM_EPI_WARPS * wbytes;
+  {
+    const int ktot = (g.mode == 0 ? g.K1 + g.K2 : g.KH * g.KW * g.K1);
+    const int stage64 = 2 * BM * 128 + 2 * p.bn * 128;
+    const int pref = bk_setting();
+    p.bk = 32;
+    // channels that do not fill the last 64-wide block (196 -> 256 instead of 224): the extra weight traffic and MMA
+    // work only pays for narrow tiles, where the A operand dominates (measured: 196 -> 196 slower, 196 -> 128 faster)
+    const bool pad_ok = cdiv(g.K1, 64) * 64 == cdiv(g.K1, 32) * 32 || p.bn <= 128;
+    if (tma_epi && pref != 32 && (pref == 64 || (ktot >= 256 && pad_ok)) && (g.K2 == 0 || g.K1 % 64 == 0) &&
+        (SMEM_LIMIT - extra_tma) / stage64 >= 2)
+      p.bk = 64;
+  }
+  const int bkk = p.bk;
+  p.cb1 = cdiv(g.K1, bkk);
   int m_tiles;
   if (g.mode == 0) {
     GIMB_CHECK(g.M > 0, "umma_gemm: M must be positive");
     p.M = g.M;
     m_tiles = (int)cdiv64(g.M, BM);
-    GIMB_TRY(rows_map(&maps.a_hi[0], g.a.hi, g.K1, g.M, g.a.ld, BM));
-    GIMB_TRY(rows_map(&maps.a_lo[0], g.a.lo, g.K1, g.M, g.a.ld, BM));
+    GIMB_TRY(rows_map(&maps.a_hi[0], g.a.hi, g.K1, g.M, g.a.ld, BM, 1, bkk));
+    GIMB_TRY(rows_map(&maps.a_lo[0], g.a.lo, g.K1, g.M, g.a.ld, BM, 1, bkk));
     if (g.K2 > 0) {
       GIMB_CHECK(g.a2.hi && g.a2.lo, "umma_gemm: concat planes missing");
-      p.cb2 = cdiv(g.K2, BK);
-      GIMB_TRY(rows_map(&maps.a2_hi, g.a2.hi, g.K2, g.M, g.a2.ld, BM));
-      GIMB_TRY(rows_map(&maps.a2_lo, g.a2.lo, g.K2, g.M, g.a2.ld, BM));
+      p.cb2 = cdiv(g.K2, bkk);
+      GIMB_TRY(rows_map(&maps.a2_hi, g.a2.hi, g.K2, g.M, g.a2.ld, BM, 1, bkk));
+      GIMB_TRY(rows_map(&maps.a2_lo, g.a2.lo, g.K2, g.M, g.a2.ld, BM, 1, bkk));
     }
     p.num_kb = p.cb1 + p.cb2;
     p.ldk = 0;
     const uint64_t Kw = (uint64_t)g.K1 + g.K2;
     GIMB_CHECK((uint64_t)g.b.ld >= Kw, "umma_gemm: weight pitch smaller than K");
-    GIMB_TRY(rows_map(&maps.b_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn));
-    GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn));
+    GIMB_TRY(rows_map(&maps.b_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn, 1, bkk));
+    GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn, 1, bkk));
   } else {
     GIMB_CHECK(g.K2 == 0, "umma_gemm: concat only in row mode");
     GIMB_CHECK(g.stride == 1 || (g.H % 2 == 0 && g.W % 2 == 0), "umma_gemm: stride-2 needs even H, W");
@@ -1470,30 +1527,22 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
       const uint64_t s = g.stride;
       uint64_t dims[4] = {(uint64_t)g.K1, (uint64_t)g.W / s, (uint64_t)g.H / s, (uint64_t)g.B};
       uint64_t strides[3] = {s * ld * 2, s * (uint64_t)g.W * ld * 2, (uint64_t)g.H * g.W * ld * 2};
-      uint32_t box[4] = {BK, TW, TH, 1};
+      uint32_t box[4] = {(uint32_t)bkk, TW, TH, 1};
       const size_t off = ((size_t)py * g.W + px) * ld;
       GIMB_TRY(make_map(&maps.a_hi[v], g.a.hi + off, 4, dims, strides, box));
       GIMB_TRY(make_map(&maps.a_lo[v], g.a.lo + off, 4, dims, strides, box));
     }
     const uint64_t Kw = (uint64_t)g.KH * g.KW * g.ldk;
     GIMB_CHECK((uint64_t)g.b.ld >= Kw, "umma_gemm: weight pitch smaller than K");
-    GIMB_TRY(rows_map(&maps.b_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn));
-    GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn));
+    GIMB_TRY(rows_map(&maps.b_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn, 1, bkk));
+    GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn, 1, bkk));
   }
-  p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * BK * 2;
-  const bool tma_epi = tma_epilogue_setting();
-  const bool want_f32 = g.out_f32 != nullptr, want_planes = g.out.hi != nullptr;
-  const bool any_res = g.residual != nullptr || g.residual_planes.hi != nullptr;
+  p.stage_bytes = 2 * BM * bkk * 2 + 2 * p.bn * bkk * 2;
   int extra;  // shared memory beside the operand ring
-  int wbytes = 0;  // TMA epilogue: staging bytes per epilogue warp (must match StageLayout<OUT> of the launched variant)
   p.res_stage = 0;
   if (tma_epi) {
-    // [ring][barriers 512][LayerNorm exchange 2048][pad 512][8 warps x staging tiles (4 KB per staged tensor)]
     GIMB_CHECK(g.act_split % 32 == 0, "umma_gemm: act_split must be a multiple of 32");
-    // the kernel variants with a residual slot reserve it even when no residual is given
-    const bool res_slot = any_res || (want_f32 && want_planes);
-    wbytes = STG_BLOCK * ((res_slot ? 1 : 0) + (want_f32 ? 1 : 0) + (want_planes ? 1 : 0));
-    extra = 1024 + 3072 + NUM_EPI_WARPS * wbytes;
+    extra = extra_tma;
     const uint64_t Mrows = (uint64_t)(g.mode == 0 ? g.M : (int64_t)g.B * g.OH * g.OW);
     if (want_f32) GIMB_TRY(block_map(&maps.o_f32, g.out_f32, true, g.mode, g.N, g.N, Mrows, g.B, g.OH, g.OW));
     if (want_planes) {
@@ -1522,11 +1571,11 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   }
   p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - extra) / p.stage_bytes);
   p.stages = std::max(2, std::min(p.stages, std::max(3, p.num_kb + 1)));
-  p.stg_off = p.stages * p.stage_bytes + 3072;
+  p.stg_off = p.stages * p.stage_bytes + fixed_tma;
   p.num_tiles = m_tiles * p.n_tiles;
   // K <= 128: one in-TMEM chunk (24 accumulation steps keep the truncation bias at the fp32-FFMA level and save a
   // drain hand-shake per tile); longer K: chunks of CHUNK_KB k-blocks
-  p.chunk_kb = p.num_kb <= 4 ? p.num_kb : chunk_kb_setting();
+  p.chunk_kb = p.num_kb * bkk <= 128 ? p.num_kb : std::max(1, chunk_kb_setting() * 32 / bkk);
   p.chunk_kb = std::max(1, std::min(p.chunk_kb, p.stages - 1));  // a chunk's stages stay resident for both MMA passes
   p.num_chunks = cdiv(p.num_kb, p.chunk_kb);
   p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
@@ -1547,8 +1596,8 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     const int m_even = (m_tiles + 1) / 2 * 2;  // an odd tile count gets one dummy tile (TMA OOB zero fill, masked stores)
     p.num_tiles = m_even * p.n_tiles;
     const uint64_t Kw = g.mode == 0 ? (uint64_t)g.K1 + g.K2 : (uint64_t)g.KH * g.KW * g.ldk;
-    GIMB_TRY(rows_map(&maps.bh_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn / 2));
-    GIMB_TRY(rows_map(&maps.bh_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn / 2));
+    GIMB_TRY(rows_map(&maps.bh_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn / 2, 1, bkk));
+    GIMB_TRY(rows_map(&maps.bh_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn / 2, 1, bkk));
   }
   const int smem = p.stages * p.stage_bytes + extra;
   GIMB_CHECK(smem <= SMEM_LIMIT, "umma_gemm: shared memory plan %d B exceeds the limit", smem);
@@ -1647,12 +1696,14 @@ __global__ void __launch_bounds__(32, 1) tma_probe_kernel(const __grid_constant_
         const int bk = variant == 0 ? 32 : 64;
         const int kb = (i * boxes + b) % (256 / bk);
         tma_load_3d(dst + b * box_bytes, &map, bar, kb * bk, t * 128, 0);
-      } else {           // conv mode: tensor [4][240][320][64 ch]; boxes are taps of an 8 x 16 patch
-        const int bk = variant == 2 ? 32 : 64;
-        const int img = t / 600, r = t % 600, th = r / 20, tw = r % 20;
+      } else {           // conv mode: tensor [4][240][320][64 ch]; boxes are taps of a TH x TW patch (TH * TW = 128)
+        const int bk = (variant & 1) ? 64 : 32;
+        const int tw = variant < 4 ? 16 : (variant < 6 ? 32 : 64), th = 128 / tw;
+        const int tiles_w = 320 / tw, per_img = tiles_w * (240 / th);
+        const int img = t / per_img, r = t % per_img, ty = r / tiles_w, tx = r % tiles_w;
         const int tap = (i * boxes + b) % (9 * (64 / bk));
         const int cb = tap % (64 / bk), kk = tap / (64 / bk);
-        tma_load_4d(dst + b * box_bytes, &map, bar, cb * bk, tw * 16 + kk % 3 - 1, th * 8 + kk / 3 - 1, img);
+        tma_load_4d(dst + b * box_bytes, &map, bar, cb * bk, tx * tw + kk % 3 - 1, ty * th + kk / 3 - 1, img);
       }
     }
   };
@@ -1665,7 +1716,7 @@ __global__ void __launch_bounds__(32, 1) tma_probe_kernel(const __grid_constant_
 }  // namespace
 
 int tma_probe(Ctx& ctx, int variant, int iters, float* gbps) {
-  GIMB_CHECK(variant >= 0 && variant < 4 && iters > 0, "tma_probe: bad arguments");
+  GIMB_CHECK(variant >= 0 && variant < 8 && iters > 0, "tma_probe: bad arguments");
   const bool conv = variant >= 2, wide = variant & 1;
   const size_t elems = conv ? (size_t)4 * 240 * 320 * 64 : (size_t)65536 * 256;
   __half* buf = nullptr;
@@ -1683,9 +1734,10 @@ int tma_probe(Ctx& ctx, int variant, int iters, float* gbps) {
     gd[0] = 256; gd[1] = 65536; gd[2] = 1; gs[0] = 512; gs[1] = 512ull * 65536;
     bx[0] = bk; bx[1] = 128; bx[2] = 1;
   } else {
+    const cuuint32_t tw = variant < 4 ? 16 : (variant < 6 ? 32 : 64);
     rank = 4; n_tiles = 4 * 600;
     gd[0] = 64; gd[1] = 320; gd[2] = 240; gd[3] = 4; gs[0] = 128; gs[1] = 128ull * 320; gs[2] = 128ull * 320 * 240;
-    bx[0] = bk; bx[1] = 16; bx[2] = 8; bx[3] = 1;
+    bx[0] = bk; bx[1] = tw; bx[2] = 128 / tw; bx[3] = 1;
   }
   CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, buf, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1739,6 +1791,7 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   p.bn = corr_bn();
   p.n_tiles = cdiv(c.S, p.bn);
   if (c.S < p.bn) p.bn = cdiv(c.S, 16) * 16;
+  p.bk = BK;
   p.K1 = c.C; p.cb1 = c.C / BK; p.cb2 = 0; p.num_kb = p.cb1;
   p.KH = p.KW = 1; p.stride = 1; p.pad = 0;
   p.M = c.L;

@@ -6,7 +6,9 @@ import torch
 from gim_b200 import _lib
 
 NAMES = ["rows, 64-B box rows (BK=32, SW64)", "rows, 128-B box rows (BK=64, SW128)",
-         "conv 8x16 patches, 64-B rows", "conv 8x16 patches, 128-B rows"]
+         "conv 8x16 patches, 64-B rows", "conv 8x16 patches, 128-B rows",
+         "conv 4x32 patches, 64-B rows", "conv 4x32 patches, 128-B rows",
+         "conv 2x64 patches, 64-B rows", "conv 2x64 patches, 128-B rows"]
 lib = _lib.load()
 for v, name in enumerate(NAMES):
     g = ctypes.c_float()
