@@ -60,71 +60,95 @@ __global__ void __launch_bounds__(NTHREADS, (BN == 128) ? 1 : 2) conv_gemm_kerne
 }
 
 // ------------------------------------------------------------------------------------------- stem
-// 7x7 s2 p3, 3 -> 64.  One CTA computes a 8 x 32 output tile for all 64 channels: the 21 x 69 x 3
-// input patch and the 64 x 147 weights sit in shared memory; each thread owns one pixel x 16 channels.
-constexpr int ST_TH = 8, ST_TW = 32;
-constexpr int ST_PH = ST_TH * 2 + 5, ST_PW = ST_TW * 2 + 5;  // 21 x 69
+// 7x7 s2 p3, 3 -> 64 (networks/loftr/backbone/resnet.py:276-279 conv1 + bn1 + relu).  Persistent CTAs: the 64 x 147
+// weights are staged once per CTA, then it walks 8 x 64 output tiles.  Each thread owns two pixels (columns px and
+// px + 32 of its row) x all 64 channels: 128 FMAs per 16 broadcast weight loads, so the loop is FMA-bound instead of
+// shared-memory-bound.  The input patch is stored de-interleaved by column parity (stride-2 taps would otherwise hit
+// the banks two ways).  Per output the summation order is (kh, kw, ci), one fmaf chain.
+constexpr int ST_TH = 8, ST_TW = 64;
+constexpr int ST_PH = ST_TH * 2 + 5;          // 21 input rows
+constexpr int ST_PWH = ST_TW + 3;             // 67 columns of each parity (133 input columns)
+constexpr int ST_PITCH = ST_PWH + 1;
 
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in, int B, int H, int W,
-                                                   const float* __restrict__ w, const float* __restrict__ scale,
-                                                   const float* __restrict__ bias, float* __restrict__ out,
-                                                   const PlanesDev sp) {
+__global__ void __launch_bounds__(256, 1) stem_kernel(const float* __restrict__ in, int B, int H, int W,
+                                                      const float* __restrict__ w, const float* __restrict__ scale,
+                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                      const PlanesDev sp, int tiles_x, int tiles_y) {
   extern __shared__ __align__(16) float st_smem[];
   float (*wsm)[64] = reinterpret_cast<float (*)[64]>(st_smem);                       // [tap*3+ci][co]
-  float (*patch)[ST_PH][ST_PW + 1] = reinterpret_cast<float (*)[ST_PH][ST_PW + 1]>(st_smem + 147 * 64);  // [3]
+  float (*patch)[ST_PH][2][ST_PITCH] = reinterpret_cast<float (*)[ST_PH][2][ST_PITCH]>(st_smem + 147 * 64);  // [3]
   const int OH = H / 2, OW = W / 2;
-  const int b = blockIdx.z;
-  const int oh0 = blockIdx.y * ST_TH, ow0 = blockIdx.x * ST_TW;
   const int tid = threadIdx.x;
   for (int i = tid; i < 147 * 64; i += 256) {
-    int co = i & 63, k = i >> 6;
-    wsm[k][co] = w[co * 147 + k];
+    const int co = i / 147, k = i - co * 147;  // coalesced global read; the transposing smem write happens once per CTA
+    wsm[k][co] = w[i];
   }
-  const int ih0 = oh0 * 2 - 3, iw0 = ow0 * 2 - 3;
-  for (int i = tid; i < 3 * ST_PH * ST_PW; i += 256) {
-    int c = i / (ST_PH * ST_PW);
-    int r = i - c * (ST_PH * ST_PW);
-    int y = r / ST_PW, x = r - y * ST_PW;
-    int ih = ih0 + y, iw = iw0 + x;
-    float v = 0.f;
-    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = in[(((size_t)b * 3 + c) * H + ih) * W + iw];
-    patch[c][y][x] = v;
-  }
-  __syncthreads();
-  const int px = tid & 31;         // output column within the tile
-  const int py = (tid >> 5) & 7;   // output row within the tile (256 threads = 8 rows x 32 cols)
-  float acc[64];
+  const int px = tid & 31;   // output columns px and px + 32 of the tile
+  const int py = tid >> 5;   // output row within the tile
+  const int n_tiles = B * tiles_y * tiles_x;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int b = t / (tiles_y * tiles_x);
+    const int r0 = t - b * (tiles_y * tiles_x);
+    const int ty = r0 / tiles_x, tx = r0 - ty * tiles_x;
+    const int oh0 = ty * ST_TH, ow0 = tx * ST_TW;
+    const int ih0 = oh0 * 2 - 3, iw0 = ow0 * 2 - 3;
+    __syncthreads();  // previous tile's patch fully consumed (and, first time, the weights staged)
+    for (int i = tid; i < 3 * ST_PH * (2 * ST_PWH); i += 256) {
+      const int c = i / (ST_PH * 2 * ST_PWH);
+      const int r = i - c * (ST_PH * 2 * ST_PWH);
+      const int y = r / (2 * ST_PWH), x = r - y * (2 * ST_PWH);
+      const int ih = ih0 + y, iw = iw0 + x;
+      float v = 0.f;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = in[(((size_t)b * 3 + c) * H + ih) * W + iw];
+      patch[c][y][x & 1][x >> 1] = v;
+    }
+    __syncthreads();
+    float acc[2][64];
 #pragma unroll
-  for (int c = 0; c < 64; ++c) acc[c] = 0.f;
-  for (int kh = 0; kh < 7; ++kh)
-    for (int kw = 0; kw < 7; ++kw) {
+    for (int c = 0; c < 64; ++c) { acc[0][c] = 0.f; acc[1][c] = 0.f; }
+    for (int kh = 0; kh < 7; ++kh)
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        float v = patch[ci][py * 2 + kh][px * 2 + kw];
-        const float4* wr = reinterpret_cast<const float4*>(&wsm[(kh * 7 + kw) * 3 + ci][0]);
+      for (int kw = 0; kw < 7; ++kw) {
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          float4 ww = wr[c4];
-          acc[c4 * 4 + 0] = fmaf(v, ww.x, acc[c4 * 4 + 0]);
-          acc[c4 * 4 + 1] = fmaf(v, ww.y, acc[c4 * 4 + 1]);
-          acc[c4 * 4 + 2] = fmaf(v, ww.z, acc[c4 * 4 + 2]);
-          acc[c4 * 4 + 3] = fmaf(v, ww.w, acc[c4 * 4 + 3]);
+        for (int ci = 0; ci < 3; ++ci) {
+          // input column 2 * px + kw -> parity kw & 1, index px + kw / 2
+          const float v0 = patch[ci][py * 2 + kh][kw & 1][px + (kw >> 1)];
+          const float v1 = patch[ci][py * 2 + kh][kw & 1][px + 32 + (kw >> 1)];
+          const float4* wr = reinterpret_cast<const float4*>(&wsm[(kh * 7 + kw) * 3 + ci][0]);
+#pragma unroll
+          for (int c4 = 0; c4 < 16; ++c4) {
+            const float4 ww = wr[c4];
+            acc[0][c4 * 4 + 0] = fmaf(v0, ww.x, acc[0][c4 * 4 + 0]);
+            acc[0][c4 * 4 + 1] = fmaf(v0, ww.y, acc[0][c4 * 4 + 1]);
+            acc[0][c4 * 4 + 2] = fmaf(v0, ww.z, acc[0][c4 * 4 + 2]);
+            acc[0][c4 * 4 + 3] = fmaf(v0, ww.w, acc[0][c4 * 4 + 3]);
+            acc[1][c4 * 4 + 0] = fmaf(v1, ww.x, acc[1][c4 * 4 + 0]);
+            acc[1][c4 * 4 + 1] = fmaf(v1, ww.y, acc[1][c4 * 4 + 1]);
+            acc[1][c4 * 4 + 2] = fmaf(v1, ww.z, acc[1][c4 * 4 + 2]);
+            acc[1][c4 * 4 + 3] = fmaf(v1, ww.w, acc[1][c4 * 4 + 3]);
+          }
         }
       }
-    }
-  int oh = oh0 + py, ow = ow0 + px;
-  if (oh < OH && ow < OW) {
-    const size_t pix = ((size_t)b * OH + oh) * OW + ow;
-    float4* o = reinterpret_cast<float4*>(out + pix * 64);
+    const int oh = oh0 + py;
 #pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      float4 r;
-      r.x = fmaxf(fmaf(acc[c4 * 4 + 0], scale[c4 * 4 + 0], bias[c4 * 4 + 0]), 0.f);
-      r.y = fmaxf(fmaf(acc[c4 * 4 + 1], scale[c4 * 4 + 1], bias[c4 * 4 + 1]), 0.f);
-      r.z = fmaxf(fmaf(acc[c4 * 4 + 2], scale[c4 * 4 + 2], bias[c4 * 4 + 2]), 0.f);
-      r.w = fmaxf(fmaf(acc[c4 * 4 + 3], scale[c4 * 4 + 3], bias[c4 * 4 + 3]), 0.f);
-      if (out) o[c4] = r;
-      if (sp.hi) split4_store(sp, pix * sp.ld + c4 * 4, r.x, r.y, r.z, r.w);
+    for (int e = 0; e < 2; ++e) {
+      const int ow = ow0 + px + 32 * e;
+      if (oh < OH && ow < OW) {
+        const size_t pix = ((size_t)b * OH + oh) * OW + ow;
+        float4* o = reinterpret_cast<float4*>(out + pix * 64);
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+          const float4 bi = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+          float4 r;
+          r.x = fmaxf(fmaf(acc[e][c4 * 4 + 0], sc.x, bi.x), 0.f);
+          r.y = fmaxf(fmaf(acc[e][c4 * 4 + 1], sc.y, bi.y), 0.f);
+          r.z = fmaxf(fmaf(acc[e][c4 * 4 + 2], sc.z, bi.z), 0.f);
+          r.w = fmaxf(fmaf(acc[e][c4 * 4 + 3], sc.w, bi.w), 0.f);
+          if (out) o[c4] = r;
+          if (sp.hi) split4_store(sp, pix * sp.ld + c4 * 4, r.x, r.y, r.z, r.w);
+        }
+      }
     }
   }
 }
@@ -221,14 +245,15 @@ int stem_conv7x7(Ctx& ctx, const float* in_nchw, int B, int H, int W, const floa
                  const float* bias, float* out_nhwc, const SplitPlanes* planes) {
   if (ctx.dry) return 0;
   const PlanesDev sp = planes ? dev(*planes) : PlanesDev{nullptr, nullptr, nullptr, 0};
-  dim3 grid(cdiv(W / 2, ST_TW), cdiv(H / 2, ST_TH), B);
-  const int smem = (147 * 64 + 3 * ST_PH * (ST_PW + 1)) * (int)sizeof(float);
+  const int tiles_x = cdiv(W / 2, ST_TW), tiles_y = cdiv(H / 2, ST_TH);
+  const int grid = std::min(B * tiles_x * tiles_y, ctx.sm_count);
+  const int smem = (147 * 64 + 3 * ST_PH * 2 * ST_PITCH) * (int)sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     GIMB_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  stem_kernel<<<grid, 256, smem, ctx.stream>>>(in_nchw, B, H, W, w, scale, bias, out_nhwc, sp);
+  stem_kernel<<<grid, 256, smem, ctx.stream>>>(in_nchw, B, H, W, w, scale, bias, out_nhwc, sp, tiles_x, tiles_y);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;

@@ -87,22 +87,33 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int s0 = s_begin; s0 < s_end; s0 += KV_CHUNK) {
-    // 32 rows x (32 K + 32 V) floats = 512 float4: 2 per thread
+  // 32 rows x (32 K + 32 V) floats = 512 float4 per chunk: 2 per thread, fetched one chunk ahead into registers so the
+  // global-load latency overlaps the previous chunk's FMAs (arithmetic order unchanged)
+  auto fetch = [&](int s0, float4 (&t)[2]) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      int idx = tid + i * 256;
-      int r = idx >> 4, q4 = idx & 15;  // row, float4 index (0..7 -> K, 8..15 -> V)
-      int s = s0 + r;
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int idx = tid + i * 256;
+      const int r = idx >> 4, q4 = idx & 15;  // row, float4 index (0..7 -> K, 8..15 -> V)
+      const int s = s0 + r;
+      t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (s < s_end) {
         const float* rowp = base + (size_t)s * 2 * C + (q4 < 8 ? h * 32 + q4 * 4 : C + h * 32 + (q4 - 8) * 4);
-        t = *reinterpret_cast<const float4*>(rowp);
+        t[i] = *reinterpret_cast<const float4*>(rowp);
       }
-      if (q4 < 8) *reinterpret_cast<float4*>(&Ks[r][q4 * 4]) = t;
-      else *reinterpret_cast<float4*>(&Vs[r][(q4 - 8) * 4]) = t;
+    }
+  };
+  float4 pre[2];
+  fetch(s_begin, pre);
+  for (int s0 = s_begin; s0 < s_end; s0 += KV_CHUNK) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx >> 4, q4 = idx & 15;
+      if (q4 < 8) *reinterpret_cast<float4*>(&Ks[r][q4 * 4]) = pre[i];
+      else *reinterpret_cast<float4*>(&Vs[r][(q4 - 8) * 4]) = pre[i];
     }
     __syncthreads();
+    if (s0 + KV_CHUNK < s_end) fetch(s0 + KV_CHUNK, pre);
 #pragma unroll
     for (int r = sub; r < KV_CHUNK; r += 4) {
       const float4 k4 = *reinterpret_cast<const float4*>(&Ks[r][dq * 4]);
@@ -180,29 +191,40 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
   for (int lc = l0; lc < l1; lc += AP_ROWS) {
     const int nr = min(AP_ROWS, l1 - lc);
     __syncthreads();
-    for (int i = tid; i < nr * 64; i += 256) {
+    for (int i = tid; i < AP_ROWS * 64; i += 256) {
       const int r = i >> 6, c4 = i & 63;
-      *reinterpret_cast<float4*>(&Qs[r][c4 * 4]) =
-          *reinterpret_cast<const float4*>(q + ((size_t)b * L + lc + r) * C + c4 * 4);
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nr) t = *reinterpret_cast<const float4*>(q + ((size_t)b * L + lc + r) * C + c4 * 4);
+      *reinterpret_cast<float4*>(&Qs[r][c4 * 4]) = t;
     }
     __syncthreads();
-    for (int r = 0; r < nr; ++r) {
-      float o = 0.f, z = 0.f;
+    // four rows at a time: eight independent FMA chains per thread (one row at a time left the two 32-deep dependent
+    // chains latency-bound); each row's summation order over d is unchanged
+    for (int r = 0; r < nr; r += 4) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f}, z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int d4 = 0; d4 < 8; ++d4) {
-        const float4 q4 = *reinterpret_cast<const float4*>(&Qs[r][h * 32 + d4 * 4]);
-        o = fmaf(q4.x, kvr[d4 * 4 + 0], o); z = fmaf(q4.x, ksr[d4 * 4 + 0], z);
-        o = fmaf(q4.y, kvr[d4 * 4 + 1], o); z = fmaf(q4.y, ksr[d4 * 4 + 1], z);
-        o = fmaf(q4.z, kvr[d4 * 4 + 2], o); z = fmaf(q4.z, ksr[d4 * 4 + 2], z);
-        o = fmaf(q4.w, kvr[d4 * 4 + 3], o); z = fmaf(q4.w, ksr[d4 * 4 + 3], z);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 q4 = *reinterpret_cast<const float4*>(&Qs[r + i][h * 32 + d4 * 4]);
+          o[i] = fmaf(q4.x, kvr[d4 * 4 + 0], o[i]); z[i] = fmaf(q4.x, ksr[d4 * 4 + 0], z[i]);
+          o[i] = fmaf(q4.y, kvr[d4 * 4 + 1], o[i]); z[i] = fmaf(q4.y, ksr[d4 * 4 + 1], z[i]);
+          o[i] = fmaf(q4.z, kvr[d4 * 4 + 2], o[i]); z[i] = fmaf(q4.z, ksr[d4 * 4 + 2], z[i]);
+          o[i] = fmaf(q4.w, kvr[d4 * 4 + 3], o[i]); z[i] = fmaf(q4.w, ksr[d4 * 4 + 3], z[i]);
+        }
       }
-      const float res = o * (1.f / (z + 1e-6f)) * vlen;
-      const size_t grow = (size_t)b * L + lc + r;
-      if (msg) msg[grow * C + tid] = res;
-      if (sp.hi) {
-        const __half hh = __float2half_rn(res);
-        sp.hi[grow * sp.ld + tid] = hh;
-        sp.lo[grow * sp.ld + tid] = __float2half_rn((res - __half2float(hh)) * kSplitScale);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (r + i < nr) {
+          const float res = o[i] * (1.f / (z[i] + 1e-6f)) * vlen;
+          const size_t grow = (size_t)b * L + lc + r + i;
+          if (msg) msg[grow * C + tid] = res;
+          if (sp.hi) {
+            const __half hh = __float2half_rn(res);
+            sp.hi[grow * sp.ld + tid] = hh;
+            sp.lo[grow * sp.ld + tid] = __float2half_rn((res - __half2float(hh)) * kSplitScale);
+          }
+        }
       }
     }
   }
