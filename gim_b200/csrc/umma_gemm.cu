@@ -67,7 +67,10 @@ struct KParams {
   int acc_cols, nbuf_log2;  // TMEM ring: 2 x 256 or 4 x 128 columns
   int res_stage;     // legacy epilogue, 1: residual planes are staged per warp through smem with cp.async
   int stg_off;       // TMA epilogue: byte offset (from the 1024-aligned smem base) of the per-warp staging tiles
-  int cluster;       // 1, or 2: CTA pairs share every B (weight) tile through TMA multicast
+  int cluster;       // 1, or 2: CTA pairs
+  int pair_mma;      // cluster == 2 only.  1: tcgen05.mma.cta_group::2 - one M = 256 MMA over the pair, each CTA holds its
+                     // 128 A rows and HALF of the B rows (operand reads and TMA writes of B per SM halve);
+                     // 0: two independent M = 128 MMAs, every B tile multicast into both CTAs
   int m_tiles_real;  // cluster mode: m tiles that exist (the pair grid may carry one dummy tile)
   int n_imgs;
   unsigned idesc;
@@ -148,6 +151,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  tma_load_3d(dst, map, bar, c0, c1, c2);
+}
+__device__ __forceinline__ void tma_load_4d_cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                int c3) {
+  tma_load_4d(dst, map, bar, c0, c1, c2, c3);
+}
 __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                                uint16_t mask) {
   asm volatile(
@@ -155,6 +165,30 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
       "[%2], %6;" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
       : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: loads signal a barrier of the pair's leader CTA, MMAs span both CTAs
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -228,6 +262,27 @@ __device__ __forceinline__ void umma_f16_scaled8(uint32_t tmem_d, uint64_t adesc
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 8;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_scaled8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, 8;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
 }
 // commit that arrives on the same barrier offset in every CTA of `mask` (cluster mode: a smem stage is written by both
 // producers of the pair, so both consumers must release it)
@@ -750,16 +805,11 @@ __device__ __forceinline__ void finish_block(const KParams& p, const TMaps& maps
 
 // ---- per-group (32 rows x 32 columns per warp) bodies of the coarse-matching epilogues.  `tb` is the warp's
 // padded smem tile holding the raw accumulators row-per-lane: tb[lane * 33 + j] = 2^8 * <f0[row], f1[col j]>.
-__device__ __forceinline__ void corr_stats_group(const KParams& p, float* tb, int lane, int q, int img, int m_tile, int cbase,
-                                                 bool row_ok, bool rmasked, float& rm, float& rs) {
-  // row view (lane = row): v[j] = sim(row, cbase + j), straight-line and register resident
-  float v[32];
+__device__ __forceinline__ void corr_stats_group(const KParams& p, float* tb, float (&v)[32], int lane, int q, int img, int m_tile,
+                                                 int cbase, bool row_ok, bool rmasked, float& rm, float& rs) {
+  // row view (lane = row): v[j] = raw accumulator of (row, cbase + j) on entry -> sim, straight-line and register resident
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 t4 = *reinterpret_cast<const float4*>(tb + lane * TBP + j4 * 4);
-    v[j4 * 4] = t4.x * p.sim_scale; v[j4 * 4 + 1] = t4.y * p.sim_scale;
-    v[j4 * 4 + 2] = t4.z * p.sim_scale; v[j4 * 4 + 3] = t4.w * p.sim_scale;
-  }
+  for (int j = 0; j < 32; ++j) v[j] *= p.sim_scale;
   if (p.mask1) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -847,7 +897,9 @@ __device__ __forceinline__ void corr_conf_group(const KParams& p, const float* t
   }
 }
 
-template <int EPI, int OUT, bool kSlowAct, bool kLN, bool kTma>
+// kPair: the tcgen05.mma.cta_group::2 build of the kernel (p.pair_mma == 1).  A separate instantiation because a kernel
+// that contains cta_group::2 instructions can only be launched with a cluster of 2.
+template <int EPI, int OUT, bool kSlowAct, bool kLN, bool kTma, bool kPair>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ TMaps maps, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -880,19 +932,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(full_bar(s), 1);
-        mbar_init(empty_bar(s), (uint32_t)p.cluster);  // released by the MMA warp of every CTA that reads/writes the stage
+        // multicast pairs: released by the MMA warp of every CTA that reads/writes the stage; pair MMA: by the leader's commit
+        mbar_init(empty_bar(s), (p.cluster == 2 && !kPair) ? 2u : 1u);
       }
       for (int b = 0; b < 4; ++b) {
         mbar_init(tfull_bar(b), 1);
-        mbar_init(tempty_bar(b), NUM_EPI_WARPS);
+        // pair MMA: the leader's issuer waits for the epilogue warps of BOTH CTAs before reusing an accumulator buffer
+        mbar_init(tempty_bar(b), kPair ? 2u * NUM_EPI_WARPS : (uint32_t)NUM_EPI_WARPS);
       }
       for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
       fence_barrier_init();
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -931,8 +991,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sA = base + stage * p.stage_bytes;
           const uint32_t sB = sA + 2 * a_plane;
-          const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, (uint32_t)p.stage_bytes);
+          // pair MMA: both CTAs' loads complete on the LEADER's barrier, which its producer arms for both stages' bytes
+          // (the peer's bytes may land before the leader arms: the phase cannot complete before the leader's arrival)
+          constexpr bool pm = kPair;
+          const uint32_t fb = pm ? mapa_cta(full_bar(stage), 0u) : full_bar(stage);
+          if (!pm) mbar_expect_tx(fb, (uint32_t)p.stage_bytes);
+          else if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.stage_bytes);
+          auto tma_load_3d = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+            if constexpr (kPair) tma_load_3d_pair(dst, m, bar, c0, c1, c2);
+            else tma_load_3d_cta(dst, m, bar, c0, c1, c2);
+          };
+          auto tma_load_4d = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+            if constexpr (kPair) tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
+            else tma_load_4d_cta(dst, m, bar, c0, c1, c2, c3);
+          };
           int bk;  // k coordinate into the weight planes
           if (p.mode == 0) {
             const int m0 = tc.m_tile * BM;
@@ -961,7 +1033,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             tma_load_4d(sA + a_plane, &maps.a_lo[view], fb, cb * p.bk, tc.ow0 + dw, tc.oh0 + dh, tc.img);
           }
           const int bb = (p.mode == 0) ? tc.img : 0;  // weights: one matrix; coarse matching: f1 of the same pair
-          if (p.cluster == 2) {
+          if (pm) {
+            // the CTA's half of the B rows (the pair MMA reads the other half from the peer's shared memory)
+            const int nh = n0 + (int)cta_rank * (p.bn >> 1);
+            tma_load_3d(sB, &maps.bh_hi, fb, bk, nh, bb);
+            tma_load_3d(sB + (b_plane >> 1), &maps.bh_lo, fb, bk, nh, bb);
+          } else if (p.cluster == 2) {
             // each CTA of the pair fetches half of the B rows and multicasts them into both CTAs' stage
             const uint32_t hoff = cta_rank * (b_plane >> 1);
             const int nh = n0 + (int)cta_rank * (p.bn >> 1);
@@ -978,7 +1055,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   } else if (warp == 1) {
     // =============================================================== MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LOW));
-    if (lane == 0) {
+    if (lane == 0 && !(kPair && cta_rank != 0)) {  // pair MMA: the leader CTA issues for both
+      constexpr bool pm = kPair;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;  // chunk counter across tiles: TMEM buffer = cc mod (number of buffers)
@@ -1007,12 +1085,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             const uint64_t dA_hi = dconst + (((base + st * p.stage_bytes) & 0x3FFFFu) >> 4);
             const uint64_t dA_lo = dA_hi + (a_plane >> 4);
             const uint64_t dB_hi = dA_hi + (a_plane >> 3);
-            const uint64_t dB_lo = dB_hi + (b_plane >> 4);
+            const uint64_t dB_lo = dB_hi + (pm ? (b_plane >> 5) : (b_plane >> 4));  // pair MMA: half-height B planes
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {  // 16 fp16 = 32 bytes = 2 address units inside the swizzled tile row
               if (kk < nk16) {
-                umma_f16(tacc, dA_hi + 2 * kk, dB_lo + 2 * kk, p.idesc, (first && kk == 0) ? 0u : 1u);
-                umma_f16(tacc, dA_lo + 2 * kk, dB_hi + 2 * kk, p.idesc, 1);
+                if constexpr (kPair) {
+                  umma_f16_pair(tacc, dA_hi + 2 * kk, dB_lo + 2 * kk, p.idesc, (first && kk == 0) ? 0u : 1u);
+                  umma_f16_pair(tacc, dA_lo + 2 * kk, dB_hi + 2 * kk, p.idesc, 1);
+                } else {
+                  umma_f16(tacc, dA_hi + 2 * kk, dB_lo + 2 * kk, p.idesc, (first && kk == 0) ? 0u : 1u);
+                  umma_f16(tacc, dA_lo + 2 * kk, dB_hi + 2 * kk, p.idesc, 1);
+                }
               }
             }
             first = false;
@@ -1025,17 +1108,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               if (kk < nk16) {
-                if (first && kk == 0) umma_f16_scaled8(tacc, dA_hi, dB_hi, p.idesc);
-                else umma_f16(tacc, dA_hi + 2 * kk, dB_hi + 2 * kk, p.idesc, 1);
+                if constexpr (kPair) {
+                  if (first && kk == 0) umma_f16_scaled8_pair(tacc, dA_hi, dB_hi, p.idesc);
+                  else umma_f16_pair(tacc, dA_hi + 2 * kk, dB_hi + 2 * kk, p.idesc, 1);
+                } else {
+                  if (first && kk == 0) umma_f16_scaled8(tacc, dA_hi, dB_hi, p.idesc);
+                  else umma_f16(tacc, dA_hi + 2 * kk, dB_hi + 2 * kk, p.idesc, 1);
+                }
               }
             }
             first = false;
             // smem stage reusable once every MMA of both passes has read it (in both CTAs of a pair)
-            if (p.cluster == 2) umma_commit_mc(empty_bar(stage), (uint16_t)3);
+            if constexpr (kPair) umma_commit_pair(empty_bar(stage));
+            else if (p.cluster == 2) umma_commit_mc(empty_bar(stage), (uint16_t)3);
             else umma_commit(empty_bar(stage));
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(tfull_bar(buf));      // chunk accumulator complete
+          if constexpr (kPair) umma_commit_pair(tfull_bar(buf));  // chunk accumulator complete (in both CTAs' TMEM)
+          else umma_commit(tfull_bar(buf));
         }
       }
     }
@@ -1048,6 +1138,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     const int half = (warp - 4) >> 2;     // which alternate 32-column groups this warp owns
     const int r_in_tile = q * 32 + lane;  // accumulator row owned by this thread
     uint32_t cc = 0;
+    // accumulator buffer drained: tell the MMA issuer (pair MMA: the leader CTA's, from both CTAs)
+    auto arrive_tempty = [&](int b) {
+      if (kPair && cta_rank != 0) mbar_arrive_cluster(mapa_cta(tempty_bar(b), 0u));
+      else mbar_arrive(tempty_bar(b));
+    };
     // TMA epilogue state: staging tiles of this warp, blocks it owns per tile, residual pipeline
     const uint32_t wb = base + (uint32_t)p.stg_off + (uint32_t)(warp - 4) * (uint32_t)StageLayout<OUT>::bytes;
     const int ng = (p.bn - half * 32 + 63) / 64;
@@ -1118,7 +1213,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             if (gi + 1 == ng) {  // last TMEM read of this warp: hand the buffer back before the block's epilogue
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(buf));
+              if (lane == 0) arrive_tempty(buf);
             }
             bool have_next;
             TileCoord tcn;
@@ -1130,7 +1225,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           if (ng == 0) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (lane == 0) arrive_tempty(buf);
           }
           ++cc;
           continue;
@@ -1161,7 +1256,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(buf));
+        if (lane == 0) arrive_tempty(buf);
       }
 
       // ---- coarse-matching sweeps (networks/loftr/utils/coarse_matching.py:111-118, 174-190).
@@ -1175,9 +1270,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         for (int gi = 0; gi < 4; ++gi) {
           const int c0 = (gi * 2 + half) * 32;
           if (c0 >= p.bn) break;              // warp-uniform
-          __syncwarp();
-          stage_group(tb, lane, acc, gi);
-          corr_stats_group(p, tb, lane, q, tc.img, tc.m_tile, n0 + c0, row_ok, rmasked, rm, rs);
+          float v[32];
+#define GIMB_TAKE(G) _Pragma("unroll") for (int j = 0; j < 32; ++j) v[j] = acc[G][j];
+          switch (gi) {  // static register indices for every case; the group loop stays rolled (instruction cache)
+            case 0: GIMB_TAKE(0) break;
+            case 1: GIMB_TAKE(1) break;
+            case 2: GIMB_TAKE(2) break;
+            default: GIMB_TAKE(3) break;
+          }
+#undef GIMB_TAKE
+          corr_stats_group(p, tb, v, lane, q, tc.img, tc.m_tile, n0 + c0, row_ok, rmasked, rm, rs);
         }
         if (row_ok) p.rowpart[row * p.row_parts + tc.n_tile * 2 + half] = make_float2(rm, rs);
         continue;
@@ -1299,7 +1401,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   __syncthreads();
   if (p.cluster == 2) cluster_sync_all();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if constexpr (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -1372,6 +1475,14 @@ int cluster_setting() {
 }
 
 // k-blocks per in-TMEM accumulation chunk (GIMB_CHUNK_KB overrides the default for experiments)
+int pair_mma_setting() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GIMB_PAIR");
+    v = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+  }
+  return v;
+}
 int chunk_kb_setting() {
   static int v = 0;
   if (!v) {
@@ -1476,8 +1587,17 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   // [alignment slack 1024][ring][barriers 512 | LayerNorm exchange 2048 (fused-LN kernels only) | pad][staging tiles]
   const int fixed_tma = g.layernorm ? 3072 : 1024;
   const int extra_tma = 1024 + fixed_tma + NUM_EPI_WARPS * wbytes;
+  // CTA pairs (cluster of 2) when the layer is big enough to fill them (GIMB_CLUSTER=1 disables).  Default: two M = 128
+  // MMAs, every B tile multicast into both CTAs.  GIMB_PAIR=mma: one tcgen05.mma.cta_group::2 over the pair, each CTA
+  // stages half of B - implemented and parity-clean, but measured 15-25 % SLOWER per layer with the chunked split scheme
+  // (profiles/r01_notes.md), so it is opt-in until that is understood.
+  const int m_tiles_plan = g.mode == 0 ? (int)cdiv64(std::max<int64_t>(g.M, 1), BM) : g.B * cdiv(g.OH, TH) * cdiv(g.OW, TW);
+  p.cluster = (cluster_setting() == 2 && m_tiles_plan >= 2 * ctx.sm_count && p.bn % 16 == 0 && p.bn >= 32) ? 2 : 1;
+  p.pair_mma = (p.cluster == 2 && tma_epi && pair_mma_setting()) ? 1 : 0;
   {
     const int ktot = (g.mode == 0 ? g.K1 + g.K2 : g.KH * g.KW * g.K1);
+    // the choice must not depend on the batch size (pairs only form for big layers): results stay bit-identical whether
+    // a pair of images is processed alone or in a batch
     const int stage64 = 2 * BM * 128 + 2 * p.bn * 128;
     const int pref = bk_setting();
     p.bk = 32;
@@ -1537,7 +1657,7 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     GIMB_TRY(rows_map(&maps.b_lo, g.b.lo, Kw, g.N, g.b.ld, p.bn, 1, bkk));
     GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn, 1, bkk));
   }
-  p.stage_bytes = 2 * BM * bkk * 2 + 2 * p.bn * bkk * 2;
+  p.stage_bytes = 2 * BM * bkk * 2 + (p.pair_mma ? 1 : 2) * p.bn * bkk * 2;  // pair MMA: each CTA stages half of B
   int extra;  // shared memory beside the operand ring
   p.res_stage = 0;
   if (tma_epi) {
@@ -1589,9 +1709,8 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   p.nb = 1;
   p.n_imgs = g.mode == 1 ? g.B : 1;
   p.m_tiles_real = m_tiles;
-  // CTA pairs (cluster of 2) share every B tile through TMA multicast: 1/3 less L2 -> SM operand traffic.  Used when
-  // the layer is big enough to fill the pairs (GIMB_CLUSTER=1 disables).
-  p.cluster = (cluster_setting() == 2 && m_tiles >= 2 * ctx.sm_count && p.bn % 16 == 0 && p.bn >= 32) ? 2 : 1;
+  GIMB_CHECK(m_tiles == m_tiles_plan, "umma_gemm: tile plan mismatch");
+  if (p.pair_mma) p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)((2 * BM) >> 4) << 24);  // M = 256 over the pair
   if (p.cluster == 2) {
     const int m_even = (m_tiles + 1) / 2 * 2;  // an odd tile count gets one dummy tile (TMA OOB zero fill, masked stores)
     p.num_tiles = m_even * p.n_tiles;
@@ -1616,11 +1735,11 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   lattr[0].id = cudaLaunchAttributeClusterDimension;
   lattr[0].val.clusterDim.x = p.cluster; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
   lcfg.attrs = lattr; lcfg.numAttrs = 1;
-#define GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, TMAV)                                                              \
+#define GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, TMAV, PAIRV)                                                       \
   do {                                                                                                            \
     static bool done = false;                                                                                     \
     if (!done) {                                                                                                  \
-      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, TMAV>,                            \
+      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, TMAV, PAIRV>,                     \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);                      \
       done = true;                                                                                                \
     }                                                                                                             \
@@ -1630,12 +1749,13 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
       return 1;                                                                                                   \
     }                                                                                                             \
     if (aerr == cudaSuccess)                                                                                      \
-      aerr = cudaLaunchKernelEx(&lcfg, umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, TMAV>, maps, p);             \
+      aerr = cudaLaunchKernelEx(&lcfg, umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, TMAV, PAIRV>, maps, p);      \
   } while (0)
-#define GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, LNV)                    \
-  do {                                                              \
-    if (tma_epi) GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, true);     \
-    else GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, false);            \
+#define GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, LNV)                                   \
+  do {                                                                             \
+    if (tma_epi && p.pair_mma) GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, true, true); \
+    else if (tma_epi) GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, true, false);        \
+    else GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, false, false);                    \
   } while (0)
 #define GIMB_LAUNCH_VARIANT(OUTV, SLOWV) GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, false)
   if (g.layernorm) {
@@ -1825,15 +1945,15 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
   static bool attr_done = false;
   if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = std::min(p.num_tiles, ctx.sm_count);
   if (pass == 0)
-    umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   else
-    umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;
