@@ -266,13 +266,16 @@ def run_ours(args):
     corr_launch_ms = corr_ms / 2 if corr_ms else None  # two GEMM sweeps (stats, conf) per forward
     roof = None
     traffic, traffic_src = None, None
-    try:  # DRAM bytes of the two sweeps from the committed ncu --set full capture (batch 8), scaled to this batch
-        summ = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_corr_v13_batch8_summary.json")))
-        mb = sum(float(k[f].split()[0]) for k in summ for f in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        traffic = mb * 1e6 / 8 * B
-        traffic_src = "profiles/r01_ncu_corr_v13_batch8_summary.json (dram read+write of both sweeps, batch 8) x B/8"
-    except Exception:
-        pass
+    # DRAM bytes of the two sweeps from the committed ncu --set full capture (batch 8), scaled to this batch
+    for name in ("r01_ncu_corr_final_batch8_summary.json", "r01_ncu_corr_v13_batch8_summary.json"):
+        try:
+            summ = json.load(open(os.path.join(ROOT, "profiles", name)))
+            mb = sum(float(k[f].split()[0]) for k in summ for f in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            traffic = mb * 1e6 / 8 * B
+            traffic_src = f"profiles/{name} (dram read+write of both sweeps, batch 8) x B/8"
+            break
+        except Exception:
+            continue
     if corr_ms:
         # algorithmic FLOPs counted ONCE per pair (11.796 GF) over the time of both sweeps
         ach = CORR_GFLOP_PER_PAIR * B / corr_ms  # TFLOP/s  (GF / ms)

@@ -65,7 +65,6 @@ struct KParams {
   int stages, stage_bytes;
   int num_tiles, num_kb, num_chunks, chunk_kb;
   int acc_cols, nbuf_log2;  // TMEM ring: 2 x 256 or 4 x 128 columns
-  int res_stage;     // legacy epilogue, 1: residual planes are staged per warp through smem with cp.async
   int stg_off;       // TMA epilogue: byte offset (from the 1024-aligned smem base) of the per-warp staging tiles
   int cluster;       // 1, or 2: CTA pairs
   int pair_mma;      // cluster == 2 only.  1: tcgen05.mma.cta_group::2 - one M = 256 MMA over the pair, each CTA holds its
@@ -213,11 +212,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// bulk L2 prefetch of one box (no shared-memory destination)
-__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -364,226 +358,8 @@ __device__ __forceinline__ float transpose_reduce(float (&v)[32], int lane, Op o
 struct OpMax { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
 struct OpAdd { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
 
-// ---- store epilogue of one 32 x 32 block: lane = output column, fully unrolled walk over the warp's 32 rows.
-// Row rr of the warp maps to global row g0 + (rr >> 4) * rowjump + (rr & 15) (mode 0: rowjump = 16, i.e. g0 + rr;
-// mode 1: two 16-pixel runs of the 8 x 16 patch, rowjump = OW).  Everything row-invariant is hoisted; the residual
-// block is prefetched into registers (32 independent coalesced loads in flight) before it is consumed.
+// output / residual selection of the store epilogue (kernel template parameter OUT)
 enum { OUT_F32 = 1, OUT_PLANES = 2, OUT_RESIDUAL = 4, OUT_RES_PLANES = 8 };  // RES_PLANES: residual given as fp16 planes
-
-// Vectorised walk over the warp's 32 x 32 block: lane = (row_sub = lane / 8, column quad = lane % 8); one
-// iteration covers 4 rows x 32 columns with 128-bit accesses (4 contiguous 128-byte row segments per warp
-// instruction), 8 iterations per block.  With 2 epilogue warps per scheduler the epilogue is bound by dependent-
-// issue latency, i.e. by instructions per element: the scalar (lane = column) form needed ~60 per 32 elements.
-template <int OUT, bool kSlowAct>
-__device__ __forceinline__ void store_rows(const KParams& p, const float* tb, int lane, int cbase, long long g0,
-                                           long long rowjump, unsigned valid, unsigned rmask_bits, const uint2 (&pre_rh)[8],
-                                           const uint2 (&pre_rl)[8], bool use_pre) {
-  const int rsub = lane >> 3, cq = lane & 7;
-  const int c = cbase + cq * 4;            // this lane's 4 columns c .. c+3 (N, act_split, ldp are multiples of 4)
-  const bool c_ok = c < p.N;
-  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-  float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.scale && c_ok) {
-    sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
-    bi = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-  }
-  const int act = c >= p.act_split ? p.act1 : p.act0;
-  const bool is_relu = act == ACT_RELU, is_leaky = act == ACT_LEAKY;
-  const bool plane_col = (OUT & OUT_PLANES) && c < p.ldp;
-  const bool has_res = (OUT & OUT_RESIDUAL) && p.residual != nullptr;
-  const bool has_resp = (OUT & OUT_RES_PLANES) != 0;
-  const float div = p.div;
-  float* const of = p.out_f32;
-  __half* const ohi = p.out_hi;
-  __half* const olo = p.out_lo;
-  const long long n64 = p.N, ld64 = p.ldp;
-  float4 v[8];
-#pragma unroll
-  for (int it = 0; it < 8; ++it) v[it] = *reinterpret_cast<const float4*>(tb + (it * 4 + rsub) * TBP + cq * 4);
-  if (has_res) {
-    float4 res[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + rsub;
-      const long long grow = g0 + (rr >> 4) * rowjump + (rr & 15);
-      res[it] = (c_ok && ((valid >> rr) & 1u)) ? __ldg(reinterpret_cast<const float4*>(p.residual + grow * n64 + c))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      v[it].x = fmaf(v[it].x, sc.x, bi.x) + res[it].x;
-      v[it].y = fmaf(v[it].y, sc.y, bi.y) + res[it].y;
-      v[it].z = fmaf(v[it].z, sc.z, bi.z) + res[it].z;
-      v[it].w = fmaf(v[it].w, sc.w, bi.w) + res[it].w;
-    }
-  } else if (has_resp) {
-    // identity carried as fp16 planes: x = hi + lo * 2^-8 (exact to 2^-22 relative)
-    uint2 rh[8], rl[8];
-    const long long lr64 = p.ldr;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + rsub;
-      const long long grow = g0 + (rr >> 4) * rowjump + (rr & 15);
-      const bool ld = c_ok && ((valid >> rr) & 1u);
-      if (use_pre) {  // staged by cp.async and already in registers (zero-filled where invalid)
-        rh[it] = pre_rh[it];
-        rl[it] = pre_rl[it];
-      } else {
-        rh[it] = ld ? *reinterpret_cast<const uint2*>(p.res_hi + grow * lr64 + c) : make_uint2(0u, 0u);
-        rl[it] = ld ? *reinterpret_cast<const uint2*>(p.res_lo + grow * lr64 + c) : make_uint2(0u, 0u);
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&rh[it].x));
-      const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&rh[it].y));
-      const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&rl[it].x));
-      const float2 l23 = __half22float2(*reinterpret_cast<const __half2*>(&rl[it].y));
-      v[it].x = fmaf(v[it].x, sc.x, bi.x) + fmaf(l01.x, 1.f / kSplitScale, h01.x);
-      v[it].y = fmaf(v[it].y, sc.y, bi.y) + fmaf(l01.y, 1.f / kSplitScale, h01.y);
-      v[it].z = fmaf(v[it].z, sc.z, bi.z) + fmaf(l23.x, 1.f / kSplitScale, h23.x);
-      v[it].w = fmaf(v[it].w, sc.w, bi.w) + fmaf(l23.y, 1.f / kSplitScale, h23.y);
-    }
-  } else {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      v[it].x = fmaf(v[it].x, sc.x, bi.x);
-      v[it].y = fmaf(v[it].y, sc.y, bi.y);
-      v[it].z = fmaf(v[it].z, sc.z, bi.z);
-      v[it].w = fmaf(v[it].w, sc.w, bi.w);
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + rsub;
-    float x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (kSlowAct) {
-        if (act == ACT_ELU1) {  // elu(x) + 1, straight-line (exp on the clamped argument, then select)
-          const float ex = expf(fminf(x[e], 0.f));
-          x[e] = x[e] > 0.f ? x[e] + 1.f : ex;
-        } else if (act == ACT_DIVS) x[e] = __fdiv_rn(x[e], div);
-        else if (is_relu) x[e] = fmaxf(x[e], 0.f);
-        else if (is_leaky) x[e] = fmaxf(x[e], 0.01f * x[e]);
-        if (!((rmask_bits >> rr) & 1u)) x[e] = 0.f;
-      } else {
-        const float r = fmaxf(x[e], 0.f), l = fmaxf(x[e], 0.01f * x[e]);
-        x[e] = is_relu ? r : (is_leaky ? l : x[e]);
-      }
-      if (!c_ok) x[e] = 0.f;  // pad channels of the fp16 planes are zero
-    }
-    const bool ok = (valid >> rr) & 1u;
-    const long long grow = g0 + (rr >> 4) * rowjump + (rr & 15);
-    if ((OUT & OUT_F32) && ok && c_ok) *reinterpret_cast<float4*>(of + grow * n64 + c) = make_float4(x[0], x[1], x[2], x[3]);
-    if (OUT & OUT_PLANES) {
-      const __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
-      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-      const __half2 l01 = __floats2half2_rn((x[0] - f01.x) * kSplitScale, (x[1] - f01.y) * kSplitScale);
-      const __half2 l23 = __floats2half2_rn((x[2] - f23.x) * kSplitScale, (x[3] - f23.y) * kSplitScale);
-      if (ok && plane_col) {
-        uint2 uh, ul;
-        uh.x = *reinterpret_cast<const unsigned int*>(&h01); uh.y = *reinterpret_cast<const unsigned int*>(&h23);
-        ul.x = *reinterpret_cast<const unsigned int*>(&l01); ul.y = *reinterpret_cast<const unsigned int*>(&l23);
-        *reinterpret_cast<uint2*>(ohi + grow * ld64 + c) = uh;
-        *reinterpret_cast<uint2*>(olo + grow * ld64 + c) = ul;
-      }
-    }
-  }
-}
-
-// L2 prefetch of the residual block a warp will consume in a LATER tile: lane = row, one 128-byte line per owned
-// 32-column group.
-__device__ __forceinline__ void prefetch_residual(const KParams& p, const TileCoord& tc, int lane, int q, int half) {
-  long long g0, rowjump;
-  bool ok;
-  if (p.mode == 0) {
-    g0 = (long long)tc.m_tile * BM + q * 32;
-    rowjump = 16;
-    ok = g0 + lane < p.M;
-  } else {
-    const int oh = tc.oh0 + q * 2, ow = tc.ow0;
-    g0 = ((long long)tc.img * p.OH + oh) * p.OW + ow;
-    rowjump = p.OW;
-    ok = (oh + (lane >> 4) < p.OH) && (ow + (lane & 15) < p.OW) && tc.img < p.n_imgs;
-  }
-  if (!ok) return;
-  const long long grow = g0 + (lane >> 4) * rowjump + (lane & 15);
-  const int n0 = tc.n_tile * p.bn;
-#pragma unroll
-  for (int gi = 0; gi < 4; ++gi) {
-    const int c0 = (gi * 2 + half) * 32;
-    if (c0 < p.bn && n0 + c0 < p.N) {
-      if (p.residual) {
-        const float* ptr = p.residual + grow * (long long)p.N + n0 + c0;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-      } else {
-        const __half* ph = p.res_hi + grow * (long long)p.ldr + n0 + c0;
-        const __half* pl = p.res_lo + grow * (long long)p.ldr + n0 + c0;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ph));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
-      }
-    }
-  }
-}
-
-constexpr int RES_BUF_BYTES = 4096;  // one 32 x 32 block of both residual planes
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// issue the cp.async copies of the residual block (rows of this warp's quadrant, columns cbase .. cbase+31) into `buf`
-__device__ __forceinline__ void issue_residual_block(const KParams& p, const TileCoord& tc, int lane, int q, int cbase,
-                                                     uint8_t* buf) {
-  long long g0, rowjump;
-  int oh = 0, ow = 0;
-  if (p.mode == 0) {
-    g0 = (long long)tc.m_tile * BM + q * 32;
-    rowjump = 16;
-  } else {
-    oh = tc.oh0 + q * 2; ow = tc.ow0;
-    g0 = ((long long)tc.img * p.OH + oh) * p.OW + ow;
-    rowjump = p.OW;
-  }
-  const uint32_t sbuf = smem_u32(buf);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int idx = lane + 32 * i;       // 256 x 16-byte pieces: [plane][row][4 segments of 8 halves]
-    const int plane = idx >> 7, row = (idx >> 2) & 31, seg = idx & 3;
-    bool ok;
-    if (p.mode == 0) ok = g0 + row < p.M;
-    else ok = (oh + (row >> 4) < p.OH) && (ow + (row & 15) < p.OW) && tc.img < p.n_imgs;
-    const int c = cbase + seg * 8;
-    ok = ok && c < p.N;
-    const long long grow = g0 + (row >> 4) * rowjump + (row & 15);
-    const __half* src = (plane ? p.res_lo : p.res_hi) + (ok ? grow * (long long)p.ldr + c : 0);
-    cp_async16(sbuf + plane * 2048 + row * 64 + seg * 16, src, ok ? 16 : 0);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-template <int OUT, bool kSlowAct>
-__device__ __forceinline__ void store_group(const KParams& p, const float* tb, int lane, int q, const TileCoord& tc, int cbase,
-                                            const uint2 (&pre_rh)[8], const uint2 (&pre_rl)[8], bool use_pre) {
-  long long g0, rowjump;
-  bool my_ok;  // validity of row rr == lane
-  if (p.mode == 0) {
-    g0 = (long long)tc.m_tile * BM + q * 32;
-    rowjump = 16;
-    my_ok = g0 + lane < p.M;
-  } else {
-    const int oh = tc.oh0 + q * 2, ow = tc.ow0;
-    g0 = ((long long)tc.img * p.OH + oh) * p.OW + ow;
-    rowjump = p.OW;
-    my_ok = (oh + (lane >> 4) < p.OH) && (ow + (lane & 15) < p.OW) && tc.img < p.n_imgs;
-  }
-  const unsigned valid = __ballot_sync(0xffffffffu, my_ok);
-  unsigned rmask_bits = 0xffffffffu;
-  if (kSlowAct && p.row_mask) {  // row masks only occur on the q / kv projections (slow-activation variant)
-    const long long grow = g0 + (lane >> 4) * rowjump + (lane & 15);
-    rmask_bits = __ballot_sync(0xffffffffu, my_ok && p.row_mask[grow] != 0);
-  }
-  store_rows<OUT, kSlowAct>(p, tb, lane, cbase, g0, rowjump, valid, rmask_bits, pre_rh, pre_rl, use_pre);
-}
 
 // Copy one of the four register-resident 32-column accumulator groups into the warp's smem tile.  The group loop in
 // the epilogues is deliberately NOT unrolled (one copy of the per-group code keeps the SASS small enough for the
@@ -899,8 +675,9 @@ __device__ __forceinline__ void corr_conf_group(const KParams& p, const float* t
 
 // kPair: the tcgen05.mma.cta_group::2 build of the kernel (p.pair_mma == 1).  A separate instantiation because a kernel
 // that contains cta_group::2 instructions can only be launched with a cluster of 2.
-template <int EPI, int OUT, bool kSlowAct, bool kLN, bool kTma, bool kPair>
+template <int EPI, int OUT, bool kSlowAct, bool kLN, bool kPair>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ TMaps maps, const KParams p) {
+  constexpr bool kTma = EPI == EPI_STORE;  // store kernels: TMA epilogue; correlation sweeps: statistics epilogues
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // stage ring, 1024-byte aligned
@@ -910,9 +687,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   float* tbuf = reinterpret_cast<float*>(gen + p.stages * p.stage_bytes + 512);  // [NUM_EPI_WARPS][32][TBP] transpose tiles
   // [2][4 quadrants][2 halves][32 rows]; the TMA epilogue has no transpose tiles, its staging tiles start at p.stg_off
   float* lnstat = kTma ? tbuf : tbuf + NUM_EPI_WARPS * 32 * TBP;
-  // OUT_RES_PLANES: per epilogue warp one 4 KB buffer ([plane hi|lo][32 rows][32 halves]) for the residual block of the
-  // next 32-column group, filled with cp.async one group ahead (the identity loads were latency-bound)
-  uint8_t* resbuf = reinterpret_cast<uint8_t*>(lnstat + 2 * NUM_EPI_WARPS * 32);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
   auto tfull_bar = [&](int b) { return bars + 128u + 8u * b; };   // up to 4 accumulator buffers
@@ -973,20 +747,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       for (int it = tile_first(p); it < tile_count(p); it += tile_step(p)) {
         const TileCoord tc = decode_tile(p, tile_linear(p, it, cta_rank));
         const int n0 = tc.n_tile * p.bn;
-        if (!kTma && (OUT & OUT_RES_PLANES) && p.res_stage && p.mode == 0) {
-          // identity block of the NEXT tile (and of the very first one) -> L2, a whole tile ahead of its consumer: the
-          // epilogue's cp.async staging then only sees L2 latency (DRAM latency under this read+write load is ~3 us)
-          const int itn = it + tile_step(p);
-          for (int pass = (it == tile_first(p)) ? 0 : 1; pass < 2; ++pass) {
-            const int itx = pass == 0 ? it : itn;
-            if (itx >= tile_count(p)) break;
-            const TileCoord tx = decode_tile(p, tile_linear(p, itx, cta_rank));
-            for (int c0 = 0; c0 < p.bn; c0 += 32) {
-              tma_prefetch_l2_3d(&maps.r_hi, tx.n_tile * p.bn + c0, tx.m_tile * BM, 0);
-              tma_prefetch_l2_3d(&maps.r_lo, tx.n_tile * p.bn + c0, tx.m_tile * BM, 0);
-            }
-          }
-        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sA = base + stage * p.stage_bytes;
@@ -1167,11 +927,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         row_ok = oh < p.OH && ow < p.OW && tc.img < p.n_imgs;
         row = ((long long)tc.img * p.OH + oh) * p.OW + ow;
       }
-      if (!kTma && EPI == EPI_STORE && (((OUT & OUT_RESIDUAL) && p.residual) || ((OUT & OUT_RES_PLANES) && !p.res_stage))) {
-        if (it == tile_first(p)) prefetch_residual(p, tc, lane, q, half);  // first tile: no lead time available
-        const int itn = it + tile_step(p);
-        if (itn < tile_count(p)) prefetch_residual(p, decode_tile(p, tile_linear(p, itn, cta_rank)), lane, q, half);
-      }
 
       // the residual block to request once block gi of this tile has been consumed: the next block of the tile, else
       // block 0 of this CTA's next tile
@@ -1300,11 +1055,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         continue;
       }
 
-      // ---- final epilogue.  The accumulator arrives row-per-lane (TMEM lane = row); global memory wants
-      // column-per-lane.  Each warp transposes its 32 x 32 block through a private padded smem tile, so every
-      // global access in store_group() is one contiguous 128-byte (fp32) or 64-byte (fp16) segment per warp
-      // instruction.  (Row-per-lane stores cost 32 LSU wavefronts per instruction.)
-      float* tb = tbuf + (warp - 4) * (32 * TBP);
+      // ---- store epilogue (multi-chunk tiles and fused LayerNorm): row-per-lane blocks through finish_block()
       if constexpr (kLN) {
         // fused LayerNorm over the full row (N == bn): this thread holds its row's columns of the alternate groups,
         // the partner warp of the quadrant the others; two-pass statistics exchanged through shared memory
@@ -1359,37 +1110,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           next_block(gi, have_next, tcn, cn);
           finish_block<OUT, kSlowAct>(p, maps, v, wb, res_bar(warp - 4), rphase, has_res, lane, q, tc,
                                       n0 + (gi * 2 + half) * 32, keep, have_next, tcn, cn);
-        }
-      } else {
-      const bool staged = (OUT & OUT_RES_PLANES) && p.res_stage;
-        uint8_t* rb = resbuf + (warp - 4) * RES_BUF_BYTES;
-        if (staged) issue_residual_block(p, tc, lane, q, n0 + half * 32, rb);  // group 0 of this warp
-#pragma unroll 1
-        for (int gi = 0; gi < 4; ++gi) {
-          const int c0 = (gi * 2 + half) * 32;
-          if (c0 >= p.bn) break;  // warp-uniform
-          uint2 rh[8], rl[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) { rh[it] = make_uint2(0u, 0u); rl[it] = make_uint2(0u, 0u); }
-          if (staged) {
-            // the residual block of this group was requested a whole group (or the drain) ago: pull it into registers,
-            // then reuse the buffer for the next group's request
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            const int rsub = lane >> 3, cq = lane & 7;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              rh[it] = *reinterpret_cast<const uint2*>(rb + (it * 4 + rsub) * 64 + cq * 8);
-              rl[it] = *reinterpret_cast<const uint2*>(rb + 2048 + (it * 4 + rsub) * 64 + cq * 8);
-            }
-            __syncwarp();
-            const int c1 = ((gi + 1) * 2 + half) * 32;
-            if (gi + 1 < 4 && c1 < p.bn) issue_residual_block(p, tc, lane, q, n0 + c1, rb);
-          }
-          __syncwarp();
-          stage_group(tb, lane, acc, gi);
-          __syncwarp();
-          store_group<OUT, kSlowAct>(p, tb, lane, q, tc, n0 + c0, rh, rl, staged);
         }
       }
     }
@@ -1493,16 +1213,6 @@ int chunk_kb_setting() {
   return v;
 }
 
-// store epilogue: bulk tensor stores / loads (default) or the LSU path (GIMB_EPI=legacy)
-bool tma_epilogue_setting() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GIMB_EPI");
-    v = (e && strcmp(e, "legacy") == 0) ? 0 : 1;
-  }
-  return v == 1;
-}
-
 // K extent of a ring stage: 0 = choose per layer (default), GIMB_BK=32 / 64 force it where possible
 int bk_setting() {
   static int v = -1;
@@ -1575,15 +1285,12 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   // K extent of a ring stage: 64 (128-byte tile rows) when the layer is K-heavy and two such stages fit - the L2 -> SM
   // path delivers ~1.5x the bytes per clock for 128-byte box rows (tools/probe_tma.py: conv patches 22.6 -> 33.3
   // B/clk/SM, row tiles 41.9 -> 49.4), and the K-heavy layers are bound by exactly that path.
-  const bool tma_epi = tma_epilogue_setting();
   const bool want_f32 = g.out_f32 != nullptr, want_planes = g.out.hi != nullptr;
   const bool any_res = g.residual != nullptr || g.residual_planes.hi != nullptr;
-  int wbytes = 0;  // TMA epilogue: staging bytes per epilogue warp (must match StageLayout<OUT> of the launched variant)
-  if (tma_epi) {
-    // the kernel variants with a residual slot reserve it even when no residual is given
-    const bool res_slot = any_res || (want_f32 && want_planes);
-    wbytes = STG_BLOCK * ((res_slot ? 1 : 0) + (want_f32 ? 1 : 0) + (want_planes ? 1 : 0));
-  }
+  // staging bytes per epilogue warp (must match StageLayout<OUT> of the launched variant); the kernel variants with a
+  // residual slot reserve it even when no residual is given
+  const bool res_slot = any_res || (want_f32 && want_planes);
+  const int wbytes = STG_BLOCK * ((res_slot ? 1 : 0) + (want_f32 ? 1 : 0) + (want_planes ? 1 : 0));
   // [alignment slack 1024][ring][barriers 512 | LayerNorm exchange 2048 (fused-LN kernels only) | pad][staging tiles]
   const int fixed_tma = g.layernorm ? 3072 : 1024;
   const int extra_tma = 1024 + fixed_tma + NUM_EPI_WARPS * wbytes;
@@ -1593,7 +1300,7 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   // (profiles/r01_notes.md), so it is opt-in until that is understood.
   const int m_tiles_plan = g.mode == 0 ? (int)cdiv64(std::max<int64_t>(g.M, 1), BM) : g.B * cdiv(g.OH, TH) * cdiv(g.OW, TW);
   p.cluster = (cluster_setting() == 2 && m_tiles_plan >= 2 * ctx.sm_count && p.bn % 16 == 0 && p.bn >= 32) ? 2 : 1;
-  p.pair_mma = (p.cluster == 2 && tma_epi && pair_mma_setting()) ? 1 : 0;
+  p.pair_mma = (p.cluster == 2 && pair_mma_setting()) ? 1 : 0;
   {
     const int ktot = (g.mode == 0 ? g.K1 + g.K2 : g.KH * g.KW * g.K1);
     // the choice must not depend on the batch size (pairs only form for big layers): results stay bit-identical whether
@@ -1604,7 +1311,7 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     // channels that do not fill the last 64-wide block (196 -> 256 instead of 224): the extra weight traffic and MMA
     // work only pays for narrow tiles, where the A operand dominates (measured: 196 -> 196 slower, 196 -> 128 faster)
     const bool pad_ok = cdiv(g.K1, 64) * 64 == cdiv(g.K1, 32) * 32 || p.bn <= 128;
-    if (tma_epi && pref != 32 && (pref == 64 || (ktot >= 256 && pad_ok)) && (g.K2 == 0 || g.K1 % 64 == 0) &&
+    if (pref != 32 && (pref == 64 || (ktot >= 256 && pad_ok)) && (g.K2 == 0 || g.K1 % 64 == 0) &&
         (SMEM_LIMIT - extra_tma) / stage64 >= 2)
       p.bk = 64;
   }
@@ -1658,11 +1365,9 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn, 1, bkk));
   }
   p.stage_bytes = 2 * BM * bkk * 2 + (p.pair_mma ? 1 : 2) * p.bn * bkk * 2;  // pair MMA: each CTA stages half of B
-  int extra;  // shared memory beside the operand ring
-  p.res_stage = 0;
-  if (tma_epi) {
-    GIMB_CHECK(g.act_split % 32 == 0, "umma_gemm: act_split must be a multiple of 32");
-    extra = extra_tma;
+  const int extra = extra_tma;  // shared memory beside the operand ring
+  GIMB_CHECK(g.act_split % 32 == 0, "umma_gemm: act_split must be a multiple of 32");
+  {
     const uint64_t Mrows = (uint64_t)(g.mode == 0 ? g.M : (int64_t)g.B * g.OH * g.OW);
     if (want_f32) GIMB_TRY(block_map(&maps.o_f32, g.out_f32, true, g.mode, g.N, g.N, Mrows, g.B, g.OH, g.OW));
     if (want_planes) {
@@ -1675,19 +1380,6 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
       GIMB_TRY(block_map(&maps.r_hi, g.residual_planes.hi, false, g.mode, ldr, ldr, Mrows, g.B, g.OH, g.OW));
       GIMB_TRY(block_map(&maps.r_lo, g.residual_planes.lo, false, g.mode, ldr, ldr, Mrows, g.B, g.OH, g.OW));
     }
-  } else {
-    // legacy: the planes-residual epilogue stages the identity block through smem (8 warps x 4 KB) when the ring still
-    // keeps >= 3 stages (or the whole K + 1) beside it
-    const int res_bytes = NUM_EPI_WARPS * 4096;
-    if (g.residual_planes.hi) {
-      const int st = (SMEM_LIMIT - SMEM_EXTRA - res_bytes) / p.stage_bytes;
-      if (st >= std::min(3, p.num_kb + 1)) p.res_stage = 1;
-    }
-    if (p.res_stage && g.mode == 0) {
-      GIMB_TRY(rows_map(&maps.r_hi, g.residual_planes.hi, g.N, g.M, g.residual_planes.ld, BM));
-      GIMB_TRY(rows_map(&maps.r_lo, g.residual_planes.lo, g.N, g.M, g.residual_planes.ld, BM));
-    }
-    extra = SMEM_EXTRA + (p.res_stage ? res_bytes : 0);
   }
   p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - extra) / p.stage_bytes);
   p.stages = std::max(2, std::min(p.stages, std::max(3, p.num_kb + 1)));
@@ -1735,27 +1427,26 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   lattr[0].id = cudaLaunchAttributeClusterDimension;
   lattr[0].val.clusterDim.x = p.cluster; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
   lcfg.attrs = lattr; lcfg.numAttrs = 1;
-#define GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, TMAV, PAIRV)                                                       \
+#define GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, PAIRV)                                                             \
   do {                                                                                                            \
     static bool done = false;                                                                                     \
     if (!done) {                                                                                                  \
-      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, TMAV, PAIRV>,                     \
+      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, PAIRV>,                           \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);                      \
       done = true;                                                                                                \
     }                                                                                                             \
-    if (TMAV && StageLayout<OUTV>::bytes != wbytes) {                                                             \
+    if (StageLayout<OUTV>::bytes != wbytes) {                                                                     \
       set_error("umma_gemm: staging plan (%d B) does not match the kernel variant (%d B)", wbytes,                \
                 (int)StageLayout<OUTV>::bytes);                                                                   \
       return 1;                                                                                                   \
     }                                                                                                             \
     if (aerr == cudaSuccess)                                                                                      \
-      aerr = cudaLaunchKernelEx(&lcfg, umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, TMAV, PAIRV>, maps, p);      \
+      aerr = cudaLaunchKernelEx(&lcfg, umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, PAIRV>, maps, p);            \
   } while (0)
-#define GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, LNV)                                   \
-  do {                                                                             \
-    if (tma_epi && p.pair_mma) GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, true, true); \
-    else if (tma_epi) GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, true, false);        \
-    else GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, false, false);                    \
+#define GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, LNV)                        \
+  do {                                                                  \
+    if (p.pair_mma) GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, true);      \
+    else GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, false);                \
   } while (0)
 #define GIMB_LAUNCH_VARIANT(OUTV, SLOWV) GIMB_LAUNCH_VARIANT_LN(OUTV, SLOWV, false)
   if (g.layernorm) {
@@ -1926,7 +1617,17 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   GIMB_TRY(rows_map(&maps.b_hi, c.f1.hi, c.C, c.S, c.f1.ld, p.bn, c.N));
   p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * BK * 2;
   p.stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - SMEM_EXTRA) / p.stage_bytes));
-  p.chunk_kb = std::max(1, std::min(chunk_kb_setting(), p.stages - 1));
+  {
+    // k-blocks accumulated inside the tensor core between fp32 drains: 4 (128 k, the same 24 accumulation steps the
+    // K <= 128 GEMM layers use; C = 256 -> two drains per tile).  Ids stay bit-exact on every golden case and the sweeps
+    // get ~9 % faster than with 64-k chunks (the drain is part of their bottleneck).  GIMB_CORR_CHUNK_KB overrides.
+    static int corr_chunk = 0;
+    if (!corr_chunk) {
+      const char* e = getenv("GIMB_CORR_CHUNK_KB");
+      corr_chunk = (e && atoi(e) > 0) ? atoi(e) : 4;
+    }
+    p.chunk_kb = std::max(1, std::min(corr_chunk, p.stages - 1));
+  }
   p.num_chunks = cdiv(p.num_kb, p.chunk_kb);
   p.idesc = (1u << 4) | ((unsigned)(p.bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
   p.acc_cols = p.bn <= 128 ? 128 : ACC_COLS;
@@ -1945,15 +1646,15 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
   static bool attr_done = false;
   if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = std::min(p.num_tiles, ctx.sm_count);
   if (pass == 0)
-    umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   else
-    umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
+    umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();
   return 0;
