@@ -174,7 +174,13 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
+        # NCCL announces its version on stdout when the communicator comes up; the contract is ONE JSON line on stdout,
+        # so everything the libraries print goes to stderr until the line itself is written
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -309,6 +315,10 @@ def run_ours(args):
         "stage_ms_per_step": stage_ms,
         "cpu_baseline": cpu,
     }
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,21 +1,27 @@
 // umma_gemm.cu - tcgen05 (5th-gen tensor core) GEMM / implicit-GEMM convolution with split-fp16 operands.
 //
 // One persistent CTA per SM, warp-specialised (see /opt/skills/guides/blackwell_cuda_programming.md "Anatomy"):
-//   warp 0      TMA producer  : cp.async.bulk.tensor (2-D/3-D row tiles or 4-D NHWC patches, OOB zero fill = conv padding)
-//                               into a ring of SWIZZLE_64B shared-memory stages, mbarrier complete_tx
+//   warp 0      TMA producer  : cp.async.bulk.tensor (3-D row tiles or 4-D NHWC patches, OOB zero fill = conv padding)
+//                               into a ring of shared-memory stages (K = 32: SWIZZLE_64B, K = 64: SWIZZLE_128B),
+//                               mbarrier complete_tx; big layers as CTA pairs (B multicast, or cta_group::2 opt-in)
 //   warp 1      MMA issuer    : one elected lane issues 3 x tcgen05.mma.kind::f16 (M=128, N<=256, K=16) per k16 step
 //                               [cross terms A_hi*B_lo + A_lo*B_hi, then A_hi*B_hi with scale-input-d 2^-8] into a
-//                               double-buffered fp32 TMEM accumulator,
+//                               ring of fp32 TMEM accumulator buffers (2 x 256 or 4 x 128 columns),
 //                               tcgen05.commit frees smem stages / publishes the accumulator
-//   warps 4..11 epilogue      : the tensor core accumulates only CHUNK_KB k-blocks at a time; the chunks are summed
-//                               in fp32 registers with round-to-nearest (tcgen05.ld, 32 lanes x 32 columns).  The MMA
-//                               accumulator truncates, and a long in-TMEM accumulation biases the result by ~K/16 ulp
-//                               (measured: 5x the fp32 FMA error at K = 1764); short chunks + RN adds keep the result
-//                               in the fp32 class.  Then 2^-8 rescale, folded-BN scale/bias, residual, activation,
-//                               row mask, fp32 store and/or re-split into fp16 planes for the next layer
+//   warps 4..11 epilogue      : the tensor core accumulates only a chunk of K at a time (64, or the whole K <= 128); the
+//                               chunks are summed in fp32 registers with round-to-nearest (tcgen05.ld, 32 lanes x 32
+//                               columns).  The MMA accumulator truncates, and a long in-TMEM accumulation biases the
+//                               result by ~K/16 ulp (measured: 5x the fp32 FMA error at K = 1764); short chunks + RN
+//                               adds keep the result in the fp32 class.  Then, row per lane: folded-BN scale/bias,
+//                               residual (bulk tensor load one block ahead), activation, row mask, and the block leaves
+//                               through the warp's swizzled staging tile with ONE bulk tensor store per tensor (fp32
+//                               and/or the re-split fp16 planes of the next layer).  The correlation sweeps
+//                               (EPI_CORR_*) replace this by their statistics epilogues.
 //
 // Tile: BM = 128 output rows (mode 0: consecutive rows; mode 1: an 8 x 16 pixel patch of one image),
-//       BN = whole N up to 256 (rounded to 16), BK = 32 fp16 (64-byte rows).
+//       BN = whole N up to 256 (rounded to 16), stage K = 32 or 64 fp16.
+// Environment knobs (measurement only): GIMB_BK=32|64, GIMB_CHUNK_KB, GIMB_CORR_CHUNK_KB, GIMB_CORR_BN=256,
+//       GIMB_CLUSTER=1 (no CTA pairs), GIMB_PAIR=mma (tcgen05.mma.cta_group::2 over the pair).
 #include <stdlib.h>
 #include <string.h>
 
