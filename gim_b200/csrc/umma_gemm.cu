@@ -345,24 +345,6 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
   return c;
 }
 
-// ------------------------------------------------------------------------------------------- kernel
-// 32-lane "transposing" reduction: on return lane l holds op over all lanes of v[l] (31 shuffles for 32 values).
-template <class Op>
-__device__ __forceinline__ float transpose_reduce(float (&v)[32], int lane, Op op) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int k = 0; k < s; ++k) {
-      const float send = up ? v[k] : v[k + s];
-      const float keep = up ? v[k + s] : v[k];
-      v[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, s));
-    }
-  }
-  return v[0];
-}
-struct OpMax { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
-struct OpAdd { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
 
 // output / residual selection of the store epilogue (kernel template parameter OUT)
 enum { OUT_F32 = 1, OUT_PLANES = 2, OUT_RESIDUAL = 4, OUT_RES_PLANES = 8 };  // RES_PLANES: residual given as fp16 planes
