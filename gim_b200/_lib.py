@@ -43,6 +43,11 @@ EXPORTS = {
     "gimb_loftr_set_profiling": (c_int, [c_void_p, c_int]),
     "gimb_loftr_set_engine": (c_int, [c_void_p, c_int]),
     "gimb_loftr_last_profile": (c_int, [c_void_p, POINTER(c_char_p), POINTER(c_float), POINTER(c_int)]),
+}
+
+# libgimb200_test.so = the product library + the layer-level test / measurement hooks (include/gimb200_test.h)
+TEST_LIB_PATH = os.path.join(HERE, "libgimb200_test.so")
+TEST_EXPORTS = {
     "gimb_bench_layer": (c_int, [c_int] * 11 + [POINTER(c_float), c_void_p]),
     "gimb_probe_tma": (c_int, [c_int, c_int, POINTER(c_float), c_void_p]),
     "gimb_test_conv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
@@ -51,6 +56,7 @@ EXPORTS = {
 }
 
 _lib = None
+_test_lib = None
 
 
 def load():
@@ -75,3 +81,23 @@ def load():
 def check(rc):
     if rc != 0:
         raise RuntimeError("libgimb200: " + load().gimb_last_error().decode(errors="replace"))
+
+
+def load_test():
+    """The test-hook superset library (tests/test_umma_gpu.py, tools/*): product symbols + TEST_EXPORTS."""
+    global _test_lib
+    if _test_lib is not None:
+        return _test_lib
+    if not os.path.isfile(TEST_LIB_PATH):
+        raise RuntimeError(f"{TEST_LIB_PATH} is missing: build it with `python -m gim_b200.build`")
+    lib = ctypes.CDLL(TEST_LIB_PATH)
+    for name, (res, args) in {**EXPORTS, **TEST_EXPORTS}.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _test_lib = lib
+    return lib
+
+
+def check_test(rc):
+    if rc != 0:
+        raise RuntimeError("libgimb200_test: " + load_test().gimb_last_error().decode(errors="replace"))

@@ -8,7 +8,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgimb200.so")
-SOURCES = ["common.cu", "conv_simt.cu", "transformer.cu", "coarse_match.cu", "fine.cu", "umma_gemm.cu", "test_hooks.cu", "loftr_api.cu"]
+TEST_LIB = os.path.join(HERE, "libgimb200_test.so")  # product objects + csrc/test_hooks.cu (include/gimb200_test.h)
+SOURCES = ["common.cu", "conv_simt.cu", "transformer.cu", "coarse_match.cu", "fine.cu", "umma_gemm.cu", "loftr_api.cu"]
+TEST_SOURCES = ["test_hooks.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -21,9 +23,9 @@ def _nvcc():
 
 
 def _stale():
-    if not os.path.isfile(LIB):
+    if not os.path.isfile(LIB) or not os.path.isfile(TEST_LIB):
         return True
-    t = os.path.getmtime(LIB)
+    t = min(os.path.getmtime(LIB), os.path.getmtime(TEST_LIB))
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gimb200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -48,10 +50,12 @@ def build_library(force=False, verbose=False):
         return obj
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        objs = list(ex.map(compile_one, SOURCES + TEST_SOURCES))
+    prod = objs[:len(SOURCES)]
+    for lib, members in ((LIB, prod), (TEST_LIB, objs)):
+        r = subprocess.run([nvcc, "-shared", "-o", lib, *members, "-lcudart"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

@@ -269,6 +269,7 @@ struct SelectArgs {
   int64_t *b_ids, *i_ids, *j_ids;
   float *mconf, *mkpts0_c, *mkpts1_c;
   int64_t* count;
+  int64_t capacity;  // rows available in the output arrays
 };
 
 // python slice semantics of `m[start:] = v` for a possibly negative start
@@ -372,7 +373,8 @@ __global__ void __launch_bounds__(256) select_scatter_kernel(const SelectArgs a)
   __syncthreads();
   int off = a.block_counts[blockIdx.x];
   for (int w = 0; w < warp; ++w) off += warp_tot[w];
-  if (f) {
+  // rows beyond the caller's capacity are counted (the host reports the overflow) but never written
+  if (f && (int64_t)off + in_warp < a.capacity) {
     int64_t pos = (int64_t)off + in_warp;
     a.b_ids[pos] = b;
     a.i_ids[pos] = i;
@@ -396,7 +398,9 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
   GIMB_CHECK(c.C % 16 == 0, "coarse_match: C must be a multiple of 16");
   GIMB_CHECK((c.mask0 == nullptr) == (c.mask1 == nullptr), "coarse_match: mask0/mask1 go together");
   GIMB_CHECK((c.scale0 == nullptr) == (c.scale1 == nullptr), "coarse_match: scale0/scale1 go together");
-  const bool tc = c.planes0 != nullptr && c.planes1 != nullptr && c.conf_matrix == nullptr;
+  // tensor-core sweeps whenever the split planes are given; an optional conf_matrix is then written by the SAME conf
+  // sweep that produces the matches (debug epilogue), so the tap and the ids come from one numerical path
+  const bool tc = c.planes0 != nullptr && c.planes1 != nullptr;
   int tiles_m = cdiv(c.L, BM), tiles_n = cdiv(c.S, BN);  // partials per column / per row
   if (tc) umma_corr_parts(c.L, c.S, &tiles_n, &tiles_m);
   const size_t NL = (size_t)c.N * c.L, NS = (size_t)c.N * c.S;
@@ -412,12 +416,8 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
   int* ext = ctx.arena.alloc<int>((size_t)c.N * 4);
   if (!ctx.dry && c.N > 0) {
     GIMB_CHECK(!ctx.arena.overflow, "coarse_match: workspace exhausted");
-    static bool attr_done = false;
-    if (!attr_done) {
-      GIMB_CUDA(cudaFuncSetAttribute(corr_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN>()));
-      GIMB_CUDA(cudaFuncSetAttribute(corr_conf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN>()));
-      attr_done = true;
-    }
+    GIMB_SMEM_OPTIN(corr_stats_kernel, smem_bytes<BN>());
+    GIMB_SMEM_OPTIN(corr_conf_kernel, smem_bytes<BN>());
     SweepArgs a;
     a.f0 = c.f0; a.f1 = c.f1; a.L = c.L; a.S = c.S; a.C = c.C;
     a.mask0 = c.mask0; a.mask1 = c.mask1;
@@ -432,7 +432,7 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
       uc.f0 = *c.planes0; uc.f1 = *c.planes1; uc.N = c.N; uc.L = c.L; uc.S = c.S; uc.C = c.C;
       uc.mask0 = c.mask0; uc.mask1 = c.mask1; uc.temperature = c.temperature; uc.thr = c.thr;
       uc.rowpart = rowpart; uc.colpart = colpart; uc.rowstat = rowstat; uc.colstat = colstat;
-      uc.rowbest = rowbest; uc.colbest = colbest;
+      uc.rowbest = rowbest; uc.colbest = colbest; uc.conf_matrix = c.conf_matrix;
       GIMB_TRY(umma_corr(ctx, uc, 0));
     } else {
       corr_stats_kernel<<<grid, NTHREADS, smem_bytes<BN>(), ctx.stream>>>(a);
@@ -473,6 +473,7 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
     s.block_counts = block_counts;
     s.b_ids = c.b_ids; s.i_ids = c.i_ids; s.j_ids = c.j_ids;
     s.mconf = c.mconf; s.mkpts0_c = c.mkpts0_c; s.mkpts1_c = c.mkpts1_c; s.count = c.count;
+    s.capacity = c.capacity;
     select_count_kernel<<<nblocks, 256, 0, ctx.stream>>>(s);
     GIMB_LAUNCH_CHECK();
     scan_blocks_kernel<<<1, 1024, 0, ctx.stream>>>(block_counts, nblocks, c.count);

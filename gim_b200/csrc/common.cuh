@@ -34,6 +34,34 @@ void set_error(const char* fmt, ...);
     if (_r != 0) return _r;    \
   } while (0)
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per device (context), so the "done"
+// state is a bit per device ordinal, set only after the call succeeded.
+#define GIMB_SMEM_OPTIN(kernel, bytes)                                                                     \
+  do {                                                                                                     \
+    static unsigned long long _done_mask = 0ull;                                                           \
+    int _dev = 0;                                                                                          \
+    GIMB_CUDA(cudaGetDevice(&_dev));                                                                       \
+    const unsigned long long _bit = 1ull << (_dev & 63);                                                   \
+    if (!(_done_mask & _bit)) {                                                                            \
+      GIMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));  \
+      _done_mask |= _bit;                                                                                  \
+    }                                                                                                      \
+  } while (0)
+
+// Every C entry point runs on its handle's device and leaves the caller's current device untouched.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Stack (bump) allocator over the caller-provided workspace.  In dry mode nothing is dereferenced:
 // the same forward code runs with launches skipped and `peak` is the workspace requirement.

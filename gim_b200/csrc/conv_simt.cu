@@ -223,12 +223,8 @@ int conv_gemm(Ctx& ctx, const ConvGemm& c) {
   GIMB_CHECK(c.in2 == nullptr || (c.KH == 1 && c.KW == 1), "conv_gemm: channel concat only for 1x1");
   GIMB_CHECK((c.scale == nullptr) == (c.bias == nullptr), "conv_gemm: scale and bias go together");
   if (ctx.dry || t.M == 0) return 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128>()));
-    GIMB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<64>()));
-    attr_done = true;
-  }
+  GIMB_SMEM_OPTIN(conv_gemm_kernel<128>, smem_bytes<128>());
+  GIMB_SMEM_OPTIN(conv_gemm_kernel<64>, smem_bytes<64>());
   if (t.N <= 64) {
     dim3 grid(cdiv(t.M, BM), cdiv(t.N, 64));
     conv_gemm_kernel<64><<<grid, NTHREADS, smem_bytes<64>(), ctx.stream>>>(p);
@@ -248,11 +244,7 @@ int stem_conv7x7(Ctx& ctx, const float* in_nchw, int B, int H, int W, const floa
   const int tiles_x = cdiv(W / 2, ST_TW), tiles_y = cdiv(H / 2, ST_TH);
   const int grid = std::min(B * tiles_x * tiles_y, ctx.sm_count);
   const int smem = (147 * 64 + 3 * ST_PH * 2 * ST_PITCH) * (int)sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
+  GIMB_SMEM_OPTIN(stem_kernel, smem);
   stem_kernel<<<grid, 256, smem, ctx.stream>>>(in_nchw, B, H, W, w, scale, bias, out_nhwc, sp, tiles_x, tiles_y);
   ctx.launches++;
   GIMB_LAUNCH_CHECK();

@@ -531,7 +531,7 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
   cm.thr = m->cfg.thr; cm.temperature = m->cfg.dsmax_temperature; cm.border = m->cfg.border_rm;
   cm.b_ids = o.b_ids; cm.i_ids = o.i_ids; cm.j_ids = o.j_ids;
   cm.mconf = o.mconf; cm.mkpts0_c = o.mkpts0_c; cm.mkpts1_c = o.mkpts1_c;
-  cm.count = dcount; cm.conf_matrix = taps.conf_matrix;
+  cm.count = dcount; cm.capacity = o.capacity; cm.conf_matrix = taps.conf_matrix;
   const ActT tok1 = view_rows(tok, (size_t)n * L);
   if (F.tc()) { cm.planes0 = tok.planes(); cm.planes1 = tok1.planes(); }
   GIMB_TRY(coarse_match(ctx, cm));
@@ -608,7 +608,8 @@ int gimb_loftr_create(const void* blob, size_t nbytes, const gimb_loftr_cfg* cfg
   int ndev = 0;
   GIMB_CUDA(cudaGetDeviceCount(&ndev));
   GIMB_CHECK(device >= 0 && device < ndev, "device %d not available (%d CUDA devices)", device, ndev);
-  GIMB_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);  // the caller's current device is restored on every exit path
+  GIMB_CHECK(guard.ok, "cudaSetDevice(%d) failed", device);
   cudaDeviceProp prop;
   GIMB_CUDA(cudaGetDeviceProperties(&prop, device));
   GIMB_CHECK(prop.major == 10, "libgimb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
@@ -670,7 +671,7 @@ int gimb_loftr_create(const void* blob, size_t nbytes, const gimb_loftr_cfg* cfg
 
 void gimb_loftr_destroy(gimb_loftr* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   if (h->dblob) cudaFree(h->dblob);
   if (h->dplanes) cudaFree(h->dplanes);
   for (auto& kv : h->pe_cache) cudaFree(kv.second);
@@ -680,7 +681,8 @@ void gimb_loftr_destroy(gimb_loftr* h) {
 
 int gimb_loftr_set_pe(gimb_loftr* h, int hc, int wc, const float* host_pe) {
   GIMB_CHECK(h && host_pe && hc > 0 && wc > 0, "gimb_loftr_set_pe: bad argument");
-  GIMB_CUDA(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  GIMB_CHECK(guard.ok, "cudaSetDevice(%d) failed", h->device);
   auto key = std::make_pair(hc, wc);
   auto it = h->pe_cache.find(key);
   float* d = nullptr;
@@ -723,7 +725,8 @@ int gimb_loftr_forward(gimb_loftr* h, const float* color0, const float* color1, 
   GIMB_CHECK(out->b_ids && out->i_ids && out->j_ids && out->mconf && out->mkpts0_c && out->mkpts1_c && out->mkpts0_f &&
                  out->mkpts1_f && out->expec_f,
              "gimb_loftr_out: every output array is required");
-  GIMB_CUDA(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  GIMB_CHECK(guard.ok, "cudaSetDevice(%d) failed", h->device);
   Ctx ctx;
   ctx.stream = (cudaStream_t)stream;
   ctx.sm_count = h->sm_count;
@@ -756,7 +759,8 @@ int gimb_loftr_forward_host(gimb_loftr* h, const float* color0, const float* col
   size_t need = 0;
   GIMB_TRY(gimb_loftr_host_staging_bytes(n, h0, w0, h1, w1, mask0 != nullptr, scale0 != nullptr, &need));
   GIMB_CHECK(dev_inputs_bytes >= need, "dev_inputs too small: %zu < %zu", dev_inputs_bytes, need);
-  GIMB_CUDA(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  GIMB_CHECK(guard.ok, "cudaSetDevice(%d) failed", h->device);
   cudaStream_t st = (cudaStream_t)stream;
   char* p = (char*)(((uintptr_t)dev_inputs + 255) / 256 * 256);
   uint64_t up = 0;

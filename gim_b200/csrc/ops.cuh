@@ -74,7 +74,8 @@ struct CoarseMatchArgs {
   int64_t *b_ids, *i_ids, *j_ids;
   float *mconf, *mkpts0_c, *mkpts1_c;
   int64_t* count;        // device scalar
-  float* conf_matrix;    // optional [N, L, S]  (forces the fp32 CUDA-core sweeps)
+  int64_t capacity = 0;  // rows available in the id / mconf / mkpts arrays (matches beyond it are counted, not written)
+  float* conf_matrix;    // optional [N, L, S] debug tap, written by whichever conf sweep runs
   // split-fp16 planes of f0 (hi, lo) / f1 (hi, lo, h8): when both are given the sweeps run on the tensor cores
   const SplitPlanes* planes0 = nullptr;
   const SplitPlanes* planes1 = nullptr;

@@ -1,9 +1,9 @@
-// test_hooks.cu - C entry points used only by tests/: run one GEMM-shaped layer through the tcgen05 kernel
+// test_hooks.cu (libgimb200_test.so only, include/gimb200_test.h) - C entry points used only by tests/ and tools/: run one GEMM-shaped layer through the tcgen05 kernel
 // and through the fp32 CUDA-core kernel on the same device buffers, so the two can be compared with a
 // float64 reference on the host side.
 #include <vector>
 
-#include "../../include/gimb200.h"
+#include "../../include/gimb200_test.h"
 #include "ops.cuh"
 #include "umma_gemm.cuh"
 

@@ -105,6 +105,7 @@ struct KParams {
   const float2* colstat;
   unsigned long long* rowbest;
   unsigned int* colbest;
+  float* conf_out;   // debug tap: full confidence matrix [nb, L, S] (null in the product path)
 };
 
 enum { EPI_STORE = 0, EPI_CORR_STATS = 1, EPI_CORR_CONF = 2 };
@@ -645,6 +646,17 @@ __device__ __forceinline__ void corr_conf_group(const KParams& p, const float* t
     if (j < ncol && (rmasked || (p.mask1 && p.mask1[gc0 + j] == 0))) x = -1e9f;
     const float t = (x - rst.x) + (x - cmax);
     cand |= (t > p.thr_log) ? (1u << j) : 0u;
+  }
+  if (p.conf_out && row_ok) {
+    // debug tap (tests): every entry with the same formula the candidates use below; lane = row, 32 columns
+    float* dst = p.conf_out + row * (long long)p.S + cbase;
+#pragma unroll 1
+    for (int j = 0; j < ncol; ++j) {
+      float x = tb[lane * TBP + j] * p.sim_scale;
+      if (rmasked || (p.mask1 && p.mask1[gc0 + j] == 0)) x = -1e9f;
+      const float2 cst = __ldg(&p.colstat[gc0 + j]);
+      dst[j] = __fdiv_rn(expf(x - cst.x), cst.y) * __fdiv_rn(expf(x - rst.x), rst.y);
+    }
   }
   while (cand) {
     const int j = __ffs(cand) - 1;
@@ -1417,12 +1429,7 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   lcfg.attrs = lattr; lcfg.numAttrs = 1;
 #define GIMB_LAUNCH_VARIANT_T(OUTV, SLOWV, LNV, PAIRV)                                                             \
   do {                                                                                                            \
-    static bool done = false;                                                                                     \
-    if (!done) {                                                                                                  \
-      aerr = cudaFuncSetAttribute(umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, PAIRV>,                           \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);                      \
-      done = true;                                                                                                \
-    }                                                                                                             \
+    GIMB_SMEM_OPTIN((umma_gemm_kernel<EPI_STORE, OUTV, SLOWV, LNV, PAIRV>), SMEM_LIMIT);                         \
     if (StageLayout<OUTV>::bytes != wbytes) {                                                                     \
       set_error("umma_gemm: staging plan (%d B) does not match the kernel variant (%d B)", wbytes,                \
                 (int)StageLayout<OUTV>::bytes);                                                                   \
@@ -1630,14 +1637,11 @@ int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass) {
   p.rowpart = c.rowpart; p.colpart = c.colpart;
   umma_corr_parts(c.L, c.S, &p.row_parts, &p.col_parts);
   p.rowstat = c.rowstat; p.colstat = c.colstat; p.rowbest = c.rowbest; p.colbest = c.colbest;
+  p.conf_out = c.conf_matrix;
   // the multiplexing TMA batch coordinate is tile.img for both operands (mode 0)
   const int smem = p.stages * p.stage_bytes + SMEM_EXTRA;
-  static bool attr_done = false;
-  if (!attr_done) {
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    GIMB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_done = true;
-  }
+  GIMB_SMEM_OPTIN((umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false>), SMEM_LIMIT);
+  GIMB_SMEM_OPTIN((umma_gemm_kernel<EPI_CORR_CONF, 0, false, false, false>), SMEM_LIMIT);
   const int grid = std::min(p.num_tiles, ctx.sm_count);
   if (pass == 0)
     umma_gemm_kernel<EPI_CORR_STATS, 0, false, false, false><<<grid, NUM_THREADS, smem, ctx.stream>>>(maps, p);

@@ -69,6 +69,7 @@ struct UmmaCorr {
   const float2* colstat = nullptr;
   unsigned long long* rowbest = nullptr;
   unsigned int* colbest = nullptr;
+  float* conf_matrix = nullptr;  // optional debug tap [N, L, S]: every confidence, written by the conf sweep
 };
 void umma_corr_parts(int L, int S, int* row_parts, int* col_parts);
 int umma_corr(Ctx& ctx, const UmmaCorr& c, int pass);

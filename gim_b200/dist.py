@@ -28,8 +28,8 @@ def gather_counts(count, device=None):
 
 
 def gather_rows(rows, dst=0):
-    """Variable-length gather of [M_r, W] float32 row blocks to `dst` (rank order preserved).
-    Returns the concatenated tensor on dst and None elsewhere."""
+    """Variable-length gather of [M_r, W] row blocks to `dst` (rank order preserved).  Only `dst` allocates the
+    world x max(M_r) receive buffers (dist.gather); the other ranks send their padded block and return None."""
     if not (dist.is_available() and dist.is_initialized()):
         return rows
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -38,15 +38,17 @@ def gather_rows(rows, dst=0):
     cap = max(counts) if counts else 0
     pad = torch.zeros(cap, width, dtype=rows.dtype, device=rows.device)
     pad[: rows.shape[0]] = rows
-    bufs = [torch.zeros_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad)  # gloo and NCCL both support all_gather of equal-size buffers
+    bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
     if rank != dst:
         return None
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
 
 
 def pack_matches(pair_ids, data):
-    """[M, 6] rows (pair_id, x0, y0, x1, y1, conf) from one forward's outputs; pair_ids maps batch index -> global id."""
+    """[M, 6] float64 rows (pair_id, x0, y0, x1, y1, conf) from one forward's outputs; pair_ids maps batch index ->
+    global pair id.  float64 keeps ids exact up to 2^53 (a float32 column would alias ids above 2^24)."""
     b = data["m_bids"].long()
-    pid = torch.as_tensor(pair_ids, device=b.device, dtype=torch.float32)[b]
-    return torch.cat([pid[:, None], data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], 1)
+    pid = torch.as_tensor(pair_ids, device=b.device, dtype=torch.float64)[b]
+    return torch.cat([pid[:, None], data["mkpts0_f"].double(), data["mkpts1_f"].double(),
+                      data["mconf"].double()[:, None]], 1)

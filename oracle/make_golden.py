@@ -138,6 +138,29 @@ def main():
         out, dt = run(model, data)
         save("synth_b2_480x640", dict(color0_u8=u8(c0), color1_u8=u8(c1)), out, dt)
 
+    # ---- round-2 cases: the configurations BASELINE.json names beyond 480x640 (inputs are regenerated from the
+    # recipe at test time, see tests/goldens.py::RECIPES; only the demo pair stores its pixels)
+    if want("demo_a_1000x1000"):  # config 1: a1 <-> a2 after demo.py:151-177 (floor to x8 -> 1000x1000), on the u8 grid
+        import torchvision.transforms.functional as TF
+        cs = []
+        for nm in ("a1", "a2"):
+            im = cv2.imread(os.path.join(REF_ROOT, "assets", "demo", nm + ".png"))[:, :, ::-1]
+            t = torch.from_numpy(np.ascontiguousarray(im).astype(np.float32).transpose(2, 0, 1) / 255.0).float()
+            size_new = tuple(int(x // 8 * 8) for x in t.shape[-2:])
+            t = TF.resize(t, size=size_new)
+            cs.append((torch.round(t.clamp(0, 1) * 255.0) / 255.0)[None])
+        c0, c1 = cs
+        data = dict(color0=c0, color1=c1, image0=c0, image1=c1)
+        out, dt = run(model, data)
+        save("demo_a_1000x1000", dict(color0_u8=u8(c0), color1_u8=u8(c1)), out, dt)
+
+    from tests.goldens import RECIPES, build_recipe  # noqa: E402
+    for name in RECIPES:
+        if want(name):
+            data = build_recipe(name)
+            out, dt = run(model, data)
+            save(name, {}, out, dt)
+
 
 if __name__ == "__main__":
     main()

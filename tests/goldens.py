@@ -14,8 +14,43 @@ CASES = ["tiny_64x96", "noise_96x128", "nomatch_flat_96x128", "diffsize_256x320_
          "masked_scaled_b2_256x320", "small_b2_240x320", "demo_a_480x640", "synth_b2_480x640"]
 
 
+# Cases whose inputs are regenerated from a recipe (gim_b200.synth is deterministic) instead of being stored:
+#   kitti_pad_b2_1240   ZEB KITTI geometry (TEST_GIM_LOFTR.sh:4, datasets/utils.py:80-126): 376x1240 content zero-padded
+#                       to 1240x1240 with mask0/mask1 and scale0/scale1, batch 2 (L = S = 155*155 = 24025)
+#   eth3d_b1_1064x1600  ETH3D geometry (TEST_GIM_LOFTR.sh:10-11): 1600-wide, batch 1 (L = S = 26600)
+#   synth_p13_p31       pairs 13 and 31 of the headline batch (bench.py: synth.make_pairs(32, 480, 640, first=0))
+RECIPES = ["kitti_pad_b2_1240", "eth3d_b1_1064x1600", "synth_p13_p31"]
+BIG_CASES = ["demo_a_1000x1000", "kitti_pad_b2_1240", "eth3d_b1_1064x1600"]
+
+
+def build_recipe(name):
+    from gim_b200 import synth
+    if name == "kitti_pad_b2_1240":
+        a0, a1 = synth.make_pairs(2, 376, 1240, first=6)
+        c0 = torch.zeros(2, 3, 1240, 1240)
+        c1 = torch.zeros(2, 3, 1240, 1240)
+        c0[:, :, :376] = a0
+        c1[:, :, :376] = a1
+        m0 = torch.zeros(2, 155, 155, dtype=torch.bool)
+        m0[:, :47] = True
+        data = dict(color0=c0, color1=c1, mask0=m0, mask1=m0.clone(),
+                    scale0=torch.tensor([[1242 / 1240, 375 / 376]] * 2), scale1=torch.tensor([[1241 / 1240, 376 / 376]] * 2))
+    elif name == "eth3d_b1_1064x1600":
+        c0, c1 = synth.make_pairs(1, 1064, 1600, first=9)
+        data = dict(color0=c0, color1=c1)
+    elif name == "synth_p13_p31":
+        a, b = synth.make_pairs(1, 480, 640, first=13), synth.make_pairs(1, 480, 640, first=31)
+        data = dict(color0=torch.cat([a[0], b[0]]), color1=torch.cat([a[1], b[1]]))
+    else:
+        raise KeyError(name)
+    data["image0"], data["image1"] = data["color0"], data["color1"]
+    return data
+
+
 def load_case(name):
     z = np.load(os.path.join(GOLD, name + ".npz"))
+    if name in RECIPES:
+        return build_recipe(name), {k: torch.from_numpy(z[k]) for k in z.files}
     data = {
         "color0": torch.from_numpy(z["color0_u8"]).float() / 255.0,
         "color1": torch.from_numpy(z["color1_u8"]).float() / 255.0,

@@ -28,6 +28,13 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
+    # the test hooks live in their own library and header, not in the product ABI
+    thdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "gimb200_test.h")).read(), flags=re.S)
+    tdecl = set(re.findall(r"\b(gimb_[a-z0-9_]+)\s*\(", thdr))
+    assert tdecl == set(_lib.TEST_EXPORTS), tdecl ^ set(_lib.TEST_EXPORTS)
+    tlib = _lib.load_test()
+    for name in tdecl:
+        assert hasattr(tlib, name) and not hasattr(lib, name), name
 
 
 def test_abi_version_and_error_string(lib):

@@ -28,7 +28,7 @@ def _worker(rank, world, port, n_pairs, out):
         data = {"m_bids": torch.zeros(m, dtype=torch.int64), "mkpts0_f": torch.full((m, 2), float(k)),
                 "mkpts1_f": torch.full((m, 2), float(k) + 0.5), "mconf": torch.full((m,), 0.25)}
         rows.append(gdist.pack_matches([k], data))
-    rows = torch.cat(rows, 0) if rows else torch.zeros(0, 6)
+    rows = torch.cat(rows, 0) if rows else torch.zeros(0, 6, dtype=torch.float64)
     counts = gdist.gather_counts(rows.shape[0])
     allrows = gdist.gather_rows(rows, dst=0)
     if rank == 0:
@@ -60,3 +60,11 @@ def test_two_rank_gather(tmp_path):
     assert torch.equal(ids, torch.sort(ids).values)
     for k in range(n_pairs):
         assert int((ids == k).sum()) == k % 5
+
+
+def test_pack_matches_keeps_large_pair_ids_exact():
+    big = (1 << 24) + 1  # not representable in float32
+    data = {"m_bids": torch.zeros(2, dtype=torch.int64), "mkpts0_f": torch.zeros(2, 2), "mkpts1_f": torch.zeros(2, 2),
+            "mconf": torch.full((2,), 0.5)}
+    rows = gdist.pack_matches([big], data)
+    assert rows.dtype == torch.float64 and rows[:, 0].long().tolist() == [big, big]

@@ -3,7 +3,7 @@
 import pytest
 import torch
 
-from tests.goldens import CASES, assert_matches_equal, load_case
+from tests.goldens import BIG_CASES, CASES, assert_matches_equal, load_case
 
 pytestmark = pytest.mark.gpu
 
@@ -29,6 +29,57 @@ def test_golden_parity(model, case):
     print(case, "M =", d["b_ids"].numel(), errs)
     assert d["mkpts0_f"].dtype == torch.float32 and d["b_ids"].dtype == torch.int64
     assert d["hw0_c"] == torch.Size((data["color0"].shape[2] // 8, data["color0"].shape[3] // 8))
+
+
+@pytest.mark.parametrize("case", BIG_CASES)
+def test_golden_parity_big_configs(model, case):
+    """BASELINE.json configs beyond 480x640, against goldens of the unmodified reference: config 1 (demo pair at
+    1000x1000: L = S = 15625 = 122 full m-tiles + a 9-row tail), the ZEB KITTI geometry (1240x1240 zero-padded, masks
+    + scales, batch 2, L = 24025) and the ZEB ETH3D geometry (1600 wide, L = 26600)."""
+    data, gold = load_case(case)
+    d = to_cuda(data)
+    model(d)
+    errs = assert_matches_equal(d, gold, what=case + ": ")
+    print(case, "M =", d["b_ids"].numel(), errs)
+
+
+def test_headline_batch_32_vs_reference_goldens(model):
+    """The bench workload itself (32 pairs @ 480x640, synth.make_pairs(32, first=0)): pairs 0, 1, 13 and 31 of the batch
+    against goldens of the unmodified reference (the reference treats pairs independently)."""
+    from gim_b200 import synth
+    c0, c1 = synth.make_pairs(32, 480, 640, first=0)
+    stored, _ = load_case("synth_b2_480x640")  # pairs 0, 1 with their pixels stored: the generator must reproduce them
+    assert torch.equal(c0[:2], stored["color0"]) and torch.equal(c1[:2], stored["color1"]), "synth is not reproducible here"
+    d = dict(color0=c0.cuda(), color1=c1.cuda(), image0=c0, image1=c1)
+    model(d)
+    assert d["b_ids"].numel() > 100000
+    keys = ("b_ids", "i_ids", "j_ids", "m_bids", "mconf", "mkpts0_c", "mkpts1_c", "mkpts0_f", "mkpts1_f", "expec_f")
+    for case, pairs in (("synth_b2_480x640", (0, 1)), ("synth_p13_p31", (13, 31))):
+        _, gold = load_case(case)
+        for local, p in enumerate(pairs):
+            sel = d["b_ids"] == p
+            gsel = gold["b_ids"] == local
+            out = {k: d[k][sel].cpu() for k in keys}
+            out["b_ids"] = out["b_ids"] - p + local
+            out["m_bids"] = out["m_bids"] - p + local
+            errs = assert_matches_equal(out, {k: gold[k][gsel] for k in keys}, what=f"batch-32 pair {p}: ")
+            print("pair", p, "M =", int(sel.sum()), errs)
+
+
+def test_tc_conf_matrix_vs_oracle_240x320(model):
+    """The confidence matrix written by the tcgen05 conf sweep (the product path's own sweeps, debug tap) against the
+    oracle at a size with several tiles per dimension (L = S = 1200) and a batch of 2."""
+    from gim_b200 import load_default_weights
+    from oracle import loftr_oracle
+    data, gold = load_case("small_b2_240x320")
+    ref = loftr_oracle.loftr_forward(load_default_weights(), data, return_intermediates=True)
+    d = to_cuda(data)
+    d["return_conf_matrix"] = True
+    model(d)
+    assert_matches_equal(d, gold, what="with conf tap: ")  # same ids as without the tap: one numerical path
+    err = (d["conf_matrix"].cpu() - ref["_inter"]["conf_matrix"]).abs().max().item()
+    print("tc conf_matrix err", err)
+    assert err < 1e-5
 
 
 def test_stage_taps_tiny(model):

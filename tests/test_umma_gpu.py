@@ -14,7 +14,7 @@ ACT = {"none": 0, "relu": 1, "leaky": 2, "elu1": 3, "divs": 4}
 def run_layer(B, H, W, C1, Cout, k, stride, C2=0, bn=False, residual=False, act="none", act1=None, split=1 << 30,
               div=1.0, mask=False, planes=True, seed=0, scale_in=1.0):
     from gim_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_test()
     g = torch.Generator().manual_seed(seed)
     x = (torch.randn(B, H, W, C1, generator=g) * scale_in).cuda()
     x2 = (torch.randn(B, H, W, C2, generator=g) * scale_in).cuda() if C2 else None
@@ -36,7 +36,7 @@ def run_layer(B, H, W, C1, Cout, k, stride, C2=0, bn=False, residual=False, act=
     rc = lib.gimb_test_conv(p(x), p(x2), B, H, W, C1, C2, p(w), Cout, k, stride, p(sc), p(bi), p(res), p(rm), ACT[act], a1,
                             split, div, p(out_u), p(out_p), p(out_s), ws.data_ptr(), ws.numel(),
                             torch.cuda.current_stream().cuda_stream)
-    _lib.check(rc)
+    _lib.check_test(rc)
     torch.cuda.synchronize()
     # float64 reference
     xin = torch.cat([x, x2], -1) if C2 else x

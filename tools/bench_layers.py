@@ -37,13 +37,13 @@ LAYERS = [
 ]
 
 def main():
-    lib = _lib.load()
+    lib = _lib.load_test()
     only = sys.argv[1:]
     for (name, b, h, w, c1, c2, co, k, s, flags, act) in LAYERS:
         if only and not any(o in name for o in only):
             continue
         ms = ctypes.c_float()
-        _lib.check(lib.gimb_bench_layer(b, h, w, c1, c2, co, k, s, flags, act, 5, ctypes.byref(ms),
+        _lib.check_test(lib.gimb_bench_layer(b, h, w, c1, c2, co, k, s, flags, act, 5, ctypes.byref(ms),
                                         torch.cuda.current_stream().cuda_stream))
         pad = k // 2
         oh, ow = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
