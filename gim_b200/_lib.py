@@ -40,6 +40,7 @@ EXPORTS = {
                                         POINTER(c_uint64), c_void_p]),
     "gimb_loftr_host_staging_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "gimb_loftr_launch_count": (c_uint64, [c_void_p]),
+    "gimb_loftr_corr_fallbacks": (c_uint64, [c_void_p]),
     "gimb_loftr_set_profiling": (c_int, [c_void_p, c_int]),
     "gimb_loftr_set_engine": (c_int, [c_void_p, c_int]),
     "gimb_loftr_last_profile": (c_int, [c_void_p, POINTER(c_char_p), POINTER(c_float), POINTER(c_int)]),

@@ -14,6 +14,10 @@
 // same values, so the `conf == max` equalities of the reference hold by construction.
 #include <algorithm>
 
+#include <stdlib.h>
+#include <string.h>
+
+#include "corr_sweep.cuh"
 #include "ops.cuh"
 #include "simt_tile.cuh"
 
@@ -401,10 +405,19 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
   // tensor-core sweeps whenever the split planes are given; an optional conf_matrix is then written by the SAME conf
   // sweep that produces the matches (debug epilogue), so the tap and the ids come from one numerical path
   const bool tc = c.planes0 != nullptr && c.planes1 != nullptr;
+  // second-generation sweeps (corr_sweep.cu) unless the caller asks for the exact online-max sweeps (fallback after a
+  // range flag, or GIMB_CORR=exact)
+  static int env_exact = -1;
+  if (env_exact < 0) {
+    const char* e = getenv("GIMB_CORR");
+    env_exact = (e && strcmp(e, "exact") == 0) ? 1 : 0;
+  }
+  const bool fast = tc && !c.exact && !env_exact && corr_sweep_supported(c.C) && c.planes0->ld == c.C && c.planes1->ld == c.C;
   int tiles_m = cdiv(c.L, BM), tiles_n = cdiv(c.S, BN);  // partials per column / per row
   if (tc) umma_corr_parts(c.L, c.S, &tiles_n, &tiles_m);
   const size_t NL = (size_t)c.N * c.L, NS = (size_t)c.N * c.S;
   size_t mark = ctx.arena.mark();
+  // workspace of the exact sweeps (also planned in dry mode: the fallback must always fit)
   float2* rowpart = ctx.arena.alloc<float2>(NL * tiles_n);
   float2* colpart = ctx.arena.alloc<float2>(NS * tiles_m);
   float2* rowstat = ctx.arena.alloc<float2>(NL);
@@ -414,8 +427,29 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
   const int nblocks = (int)cdiv64((int64_t)NL, 256);
   int* block_counts = ctx.arena.alloc<int>(nblocks);
   int* ext = ctx.arena.alloc<int>((size_t)c.N * 4);
+  // workspace of the second-generation sweeps
+  CorrSweep cs;
+  if (tc && corr_sweep_supported(c.C)) {
+    int rp, cp, Lp, Sp;
+    corr_sweep_parts(ctx, c.N, c.L, c.S, c.C, &rp, &cp, &Lp, &Sp);
+    cs.normsq = ctx.arena.alloc<float>(2 * (size_t)c.N);
+    cs.rowpart = ctx.arena.alloc<float>((size_t)rp * c.N * Lp);
+    cs.colpart = ctx.arena.alloc<float>((size_t)cp * c.N * Sp);
+    cs.rowstat = ctx.arena.alloc<float2>((size_t)c.N * Lp);
+    cs.colthr = ctx.arena.alloc<float>((size_t)c.N * Sp);
+    cs.colsum = ctx.arena.alloc<float>((size_t)c.N * Sp);
+  }
   if (!ctx.dry && c.N > 0) {
     GIMB_CHECK(!ctx.arena.overflow, "coarse_match: workspace exhausted");
+    if (c.range_flag && !fast) GIMB_CUDA(cudaMemsetAsync(c.range_flag, 0, sizeof(int), ctx.stream));
+    if (fast) {
+      GIMB_CHECK(c.range_flag != nullptr, "coarse_match: the fast sweeps need a range flag");
+      cs.f0 = *c.planes0; cs.f1 = *c.planes1; cs.f0_f32 = c.f0; cs.f1_f32 = c.f1;
+      cs.N = c.N; cs.L = c.L; cs.S = c.S; cs.C = c.C;
+      cs.mask0 = c.mask0; cs.mask1 = c.mask1; cs.temperature = c.temperature; cs.thr = c.thr;
+      cs.flag = c.range_flag; cs.rowbest = rowbest; cs.colbest = colbest; cs.conf_matrix = c.conf_matrix;
+      GIMB_TRY(corr_sweeps(ctx, cs));
+    } else {
     GIMB_SMEM_OPTIN(corr_stats_kernel, smem_bytes<BN>());
     GIMB_SMEM_OPTIN(corr_conf_kernel, smem_bytes<BN>());
     SweepArgs a;
@@ -454,6 +488,7 @@ int coarse_match(Ctx& ctx, const CoarseMatchArgs& c) {
     }
     ctx.mark("corr_conf");
     ctx.launches += 4;
+    }
 
     SelectArgs s;
     s.rowbest = rowbest; s.colbest = colbest;

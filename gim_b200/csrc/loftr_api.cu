@@ -45,6 +45,7 @@ struct gimb_loftr {
   std::map<std::pair<int, int>, float*> pe_cache;
   int64_t* host_count = nullptr;  // pinned
   uint64_t launches = 0;
+  uint64_t corr_fallbacks = 0;    // forwards that repeated the coarse matching with the exact sweeps
   int sm_count = 148;
   bool profiling = false;
   std::vector<std::pair<std::string, float>> last_profile;
@@ -361,7 +362,7 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
 
   // 3. coarse matching (loftr.py:83)
   const gimb_loftr_out& o = *f.out;
-  int64_t* dcount = A.alloc<int64_t>(1);
+  int64_t* dcount = A.alloc<int64_t>(2);  // [0] match count, [1] range flag of the fast correlation sweeps
   CoarseMatchArgs cm;
   cm.f0 = fc0; cm.f1 = fc1; cm.N = n; cm.L = L; cm.S = S; cm.C = C;
   cm.h0c = h0c; cm.w0c = w0c; cm.h1c = h1c; cm.w1c = w1c; cm.H0 = f.h0; cm.H1 = f.h1;
@@ -372,14 +373,24 @@ int forward_impl(Ctx& ctx, gimb_loftr* m, const FwdArgs& f, int64_t* m_out) {
   cm.count = dcount; cm.capacity = o.capacity; cm.conf_matrix = taps.conf_matrix;
   const ActT tok1 = view_rows(tok, (size_t)n * L);
   if (F.tc()) { cm.planes0 = tok.planes(); cm.planes1 = tok1.planes(); }
+  cm.range_flag = reinterpret_cast<int*>(dcount + 1);
   GIMB_TRY(coarse_match(ctx, cm));
   prof.mark("select_compact");
 
   // the one host synchronisation of the forward: M sizes the fine stage (reference: torch.where)
   int64_t M = 0;
   if (!ctx.dry) {
-    GIMB_CUDA(cudaMemcpyAsync(m->host_count, dcount, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx.stream));
+    GIMB_CUDA(cudaMemcpyAsync(m->host_count, dcount, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx.stream));
     GIMB_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (*reinterpret_cast<const int*>(m->host_count + 1) != 0) {
+      // a softmax sum left the safe range of the fast sweeps' fixed exponent reference: repeat the coarse matching with
+      // the exact online-max sweeps (same outputs, ~3x the sweep time; not observed on real features)
+      m->corr_fallbacks++;
+      cm.exact = true;
+      GIMB_TRY(coarse_match(ctx, cm));
+      GIMB_CUDA(cudaMemcpyAsync(m->host_count, dcount, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx.stream));
+      GIMB_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
     M = *m->host_count;
     GIMB_CHECK(M <= o.capacity, "forward: %lld matches exceed the output capacity %lld", (long long)M,
                (long long)o.capacity);
@@ -464,7 +475,7 @@ int gimb_loftr_create(const void* blob, size_t nbytes, const gimb_loftr_cfg* cfg
   }
   const char* eng = getenv("GIMB_ENGINE");
   if (eng && eng[0] == 's') m->engine = ENGINE_SIMT;
-  if (cudaMallocHost(&m->host_count, sizeof(int64_t)) != cudaSuccess) {
+  if (cudaMallocHost(&m->host_count, 2 * sizeof(int64_t)) != cudaSuccess) {
     gimb_loftr_destroy(m);
     set_error("cudaMallocHost failed");
     return 1;
@@ -613,6 +624,7 @@ int gimb_loftr_forward_host(gimb_loftr* h, const float* color0, const float* col
 }
 
 uint64_t gimb_loftr_launch_count(gimb_loftr* h) { return h ? h->launches : 0; }
+uint64_t gimb_loftr_corr_fallbacks(gimb_loftr* h) { return h ? h->corr_fallbacks : 0; }
 
 int gimb_loftr_set_engine(gimb_loftr* h, int engine) {
   GIMB_CHECK(h && (engine == ENGINE_SIMT || engine == ENGINE_TC), "gimb_loftr_set_engine: bad argument");

@@ -79,6 +79,10 @@ struct CoarseMatchArgs {
   // split-fp16 planes of f0 (hi, lo) / f1 (hi, lo, h8): when both are given the sweeps run on the tensor cores
   const SplitPlanes* planes0 = nullptr;
   const SplitPlanes* planes1 = nullptr;
+  // tcgen05 engine: the fast sweeps (corr_sweep.cu) set *range_flag (device int) when a softmax sum left the range in
+  // which their fixed exponent reference is exact; the caller then repeats the call with exact = true (online-max sweeps)
+  int* range_flag = nullptr;
+  bool exact = false;
 };
 int coarse_match(Ctx& ctx, const CoarseMatchArgs& a);
 

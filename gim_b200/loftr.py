@@ -207,6 +207,10 @@ class LoFTR(nn.Module):
     def launch_count(self):
         return int(_lib.load().gimb_loftr_launch_count(self._handle)) if self._handle else 0
 
+    def corr_fallbacks(self):
+        """Forwards that repeated the coarse matching with the exact correlation sweeps (csrc/corr_sweep.cu)."""
+        return int(_lib.load().gimb_loftr_corr_fallbacks(self._handle)) if self._handle else 0
+
     # -- forward -------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, data, taps=None):

@@ -141,6 +141,9 @@ int gimb_loftr_host_staging_bytes(int n, int h0, int w0, int h1, int w1, int wit
 /* Number of kernels this library launched on behalf of handle `h` since creation (for bench.py's
  * `gpu_launches`), and the per-stage device time of the last forward when profiling is enabled. */
 uint64_t gimb_loftr_launch_count(gimb_loftr* h);
+/* forwards of this handle that had to repeat the coarse matching with the exact (online-max) correlation sweeps because
+ * a softmax sum left the range of the fast sweeps' fixed exponent reference (csrc/corr_sweep.cu); 0 on real features */
+uint64_t gimb_loftr_corr_fallbacks(gimb_loftr* h);
 /* GEMM engine of the handle: 1 = tcgen05 tensor cores with split-fp16 operands (default),
  * 0 = fp32 CUDA-core kernels (the exact-fp32 cross-check path; ~10x slower). */
 int gimb_loftr_set_engine(gimb_loftr* h, int engine);
