@@ -272,21 +272,25 @@ def run_ours(args):
     corr_launch_ms = corr_ms / 2 if corr_ms else None  # two GEMM sweeps (stats, conf) per forward
     roof = None
     traffic, traffic_src = None, None
-    # DRAM bytes of the two sweeps from the committed ncu --set full capture (batch 8), scaled to this batch
-    for name in ("r01_ncu_corr_final_batch8_summary.json", "r01_ncu_corr_v13_batch8_summary.json"):
-        try:
-            summ = json.load(open(os.path.join(ROOT, "profiles", name)))
-            mb = sum(float(k[f].split()[0]) for k in summ for f in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-            traffic = mb * 1e6 / 8 * B
-            traffic_src = f"profiles/{name} (dram read+write of both sweeps, batch 8) x B/8"
-            break
-        except Exception:
-            continue
+    # DRAM bytes (read + write) of the two sweeps: `ncu --set full` capture of THIS command at the headline batch
+    # (profiles/r02_ncu_corr_v2_batch32_summary.json, per launch = per sweep of 32 pairs).  Other batch sizes scale
+    # the per-pair figure and say so.
+    tensor_pipe = None
+    try:
+        name, cap_b = "r02_ncu_corr_v2_batch32_summary.json", 32
+        summ = json.load(open(os.path.join(ROOT, "profiles", name)))
+        mb = sum(float(k[f].split()[0]) for k in summ for f in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        traffic = mb * 1e6 * B / cap_b
+        traffic_src = f"profiles/{name} (dram read+write of both sweeps at batch {cap_b}" + (")" if B == cap_b else f", x {B}/{cap_b})")
+        tensor_pipe = [float(k["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"].split()[0]) for k in summ]
+    except Exception:
+        pass
     if corr_ms:
         # algorithmic FLOPs counted ONCE per pair (11.796 GF) over the time of both sweeps
         ach = CORR_GFLOP_PER_PAIR * B / corr_ms  # TFLOP/s  (GF / ms)
         roof = {"bound": "tensor",
-                "kernel": "umma_gemm_kernel<EPI_CORR_STATS> + umma_gemm_kernel<EPI_CORR_CONF> (dual-softmax correlation sweeps, tcgen05)",
+                "kernel": "corr_sweep_kernel<STATS> + corr_sweep_kernel<CONF> (dual-softmax correlation sweeps, tcgen05.mma.cta_group::2; "
+                          "the time also covers the row-norm and merge helpers between them)",
                 "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                 "traffic": traffic, "traffic_unit": "bytes per forward (both sweeps)", "traffic_source": traffic_src,
                 "algorithmic_bytes": 2 * (H // 8 * W // 8) * 256 * 4 * B,
@@ -294,6 +298,7 @@ def run_ours(args):
                 "operand_format": "fp16 2-term split (hi, lo*2^8): 3 tcgen05.mma.kind::f16 per logical MAC, 2 sweeps -> "
                                   "executed MMA work = 6x the algorithmic 11.796 GF/pair",
                 "mma_tflops_executed": 6 * ach,
+                "tensor_pipe_active_pct_ncu": tensor_pipe,
                 "ms_per_launch": corr_launch_ms}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

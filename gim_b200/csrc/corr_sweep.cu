@@ -32,6 +32,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "corr_sweep.cuh"
 #include "umma_ptx.cuh"
@@ -75,6 +76,7 @@ struct CorrParams {
   unsigned long long* rowbest;
   unsigned int* colbest;
   float* conf_out;
+  long long* dbg;  // optional [grid][16] cycle counters (GIMB_CORR_DEBUG=1): where every role waits
 };
 
 __device__ __forceinline__ float pair_ref(const CorrParams& p, int img) {
@@ -84,6 +86,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
@@ -180,7 +187,18 @@ __global__ void __launch_bounds__(C_THREADS, 1) corr_sweep_kernel(const __grid_c
   __syncthreads();
   if (kPair) cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // A 512-column allocation is the whole tensor memory: its base address is 0 by construction, and using the constant
+  // keeps the MMA operands in uniform registers (the slot written by tcgen05.alloc is only read back in debug runs).
+  constexpr uint32_t tmem_base = 0u;
+  if (p.dbg != nullptr && *tmem_slot != 0u) __trap();
+  long long dbg_acc[6] = {0, 0, 0, 0, 0, 0};  // [3]: MMA warp only - b_full waits on the first tile of a unit
+  const long long dbg_t0 = clock64();
+  auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (p.dbg == nullptr) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    dbg_acc[slot] += clock64() - t0;
+  };
 
   if (warp == 0) {
     // =============================================================== TMA producer
@@ -194,22 +212,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) corr_sweep_kernel(const __grid_c
         const int m_tile = kPair ? un.mg * 2 + (int)rank : un.mg;
         for (int nt = un.n_begin; nt < un.n_end; ++nt) {
           for (int kb = 0; kb < p.num_kb; ++kb) {
-            if (nt == un.n_begin) {
-              // the resident f0 k-block: free once the MMAs of the previous unit's last tile have read it
-              mbar_wait(a_empty(kb), (ucount & 1u) ^ 1u);
-              const uint32_t dst = a_base + (uint32_t)kb * A_KB_BYTES;
-              if constexpr (kPair) {
-                const uint32_t fb = mapa_cta(a_full(kb), 0u);  // both CTAs' bytes complete on the leader's barrier
-                if (rank == 0) mbar_expect_tx(a_full(kb), 2u * A_KB_BYTES);
-                tma_load_3d_pair(dst, &maps.a_hi, fb, kb * CK, m_tile * CM, un.img);
-                tma_load_3d_pair(dst + A_PLANE_BYTES, &maps.a_lo, fb, kb * CK, m_tile * CM, un.img);
-              } else {
-                mbar_expect_tx(a_full(kb), A_KB_BYTES);
-                tma_load_3d(dst, &maps.a_hi, a_full(kb), kb * CK, m_tile * CM, un.img);
-                tma_load_3d(dst + A_PLANE_BYTES, &maps.a_lo, a_full(kb), kb * CK, m_tile * CM, un.img);
-              }
-            }
-            mbar_wait(b_empty(stage), phase ^ 1u);
+            timed_wait(b_empty(stage), phase ^ 1u, 1);
             const uint32_t sB = b_base + (uint32_t)stage * (uint32_t)p.b_stage_bytes;
             if constexpr (kPair) {
               const uint32_t fb = mapa_cta(b_full(stage), 0u);
@@ -230,46 +233,91 @@ __global__ void __launch_bounds__(C_THREADS, 1) corr_sweep_kernel(const __grid_c
   } else if (warp == 1) {
     // =============================================================== MMA issuer (pairs: the leader CTA issues for both)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(40));
-    if (lane == 0 && !(kPair && rank != 0)) {
+    // The whole warp runs the loop (warp-uniform control flow, every operand derived from kernel parameters and the
+    // shared-memory base): ptxas then keeps descriptors and addresses in UNIFORM registers and an MMA costs one UIADD
+    // plus the UTCHMMA itself.  Under `if (lane == 0)` every operand lived in a vector register and each MMA paid a
+    // 15-instruction elect / R2UR "waterfall" (~100 cycles - more than the 64 cycles an N = 128 MMA takes; measured
+    // with tools/probe_mma.py and the per-role cycle counters of GIMB_CORR_DEBUG).
+    if (!(kPair && rank != 0)) {
       int stage = 0;
       uint32_t phase = 0, ucount = 0, tcount = 0;
+      const bool leader = elect_one();
       const uint64_t dconst = make_desc_sw128(0u);
       const uint32_t b_plane = (uint32_t)p.b_stage_bytes >> 1;
-      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
-        if constexpr (kPair) umma_f16_pair(d, da, db, p.idesc, acc);
-        else umma_f16(d, da, db, p.idesc, acc);
-      };
-      auto commit = [&](uint32_t bar) {
-        if constexpr (kPair) umma_commit_pair(bar);
-        else umma_commit(bar);
+      auto wait1 = [&](uint32_t bar, uint32_t parity, int slot) {  // one lane polls, the warp re-converges
+        if (lane == 0) timed_wait(bar, parity, slot);
+        __syncwarp();
       };
       for (int u = first; u < p.units; u += step, ++ucount) {
         const Unit un = decode_unit(p, u);
         for (int nt = un.n_begin; nt < un.n_end; ++nt, ++tcount) {
           const uint32_t h = tcount & 1u, k = tcount >> 1;
-          mbar_wait(tempty((int)h), (k & 1u) ^ 1u);
+          wait1(tempty((int)h), (k & 1u) ^ 1u, 0);
           tc_fence_after();
-          const uint32_t tX = tmem_base + h * 256u, tY = tX + 128u;
+          const uint32_t tX = h * 256u, tY = tX + 128u;  // the 512-column allocation starts at TMEM address 0 (checked below)
           for (int kb = 0; kb < p.num_kb; ++kb) {
-            if (nt == un.n_begin) mbar_wait(a_full(kb), ucount & 1u);
-            mbar_wait(b_full(stage), phase);
+            if (nt == un.n_begin) wait1(a_full(kb), ucount & 1u, 1);
+            wait1(b_full(stage), phase, nt == un.n_begin ? 3 : 2);
             tc_fence_after();
             const uint64_t dA_hi = dconst + (((a_base + (uint32_t)kb * A_KB_BYTES) & 0x3FFFFu) >> 4);
             const uint64_t dA_lo = dA_hi + (A_PLANE_BYTES >> 4);
             const uint64_t dB_hi = dconst + (((b_base + (uint32_t)stage * (uint32_t)p.b_stage_bytes) & 0x3FFFFu) >> 4);
             const uint64_t dB_lo = dB_hi + (b_plane >> 4);
+            const uint32_t acc0 = kb == 0 ? 0u : 1u;
+            if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < CK / 16; ++kk) {  // 16 fp16 = 32 bytes = 2 address units inside the swizzled row
-              const uint32_t acc = (kb == 0 && kk == 0) ? 0u : 1u;
-              mma(tX, dA_hi + 2 * kk, dB_lo + 2 * kk, acc);
-              mma(tX, dA_lo + 2 * kk, dB_hi + 2 * kk, 1u);
-              mma(tY, dA_hi + 2 * kk, dB_hi + 2 * kk, acc);
+              for (int kk = 0; kk < CK / 16; ++kk) {  // 16 fp16 = 32 bytes = 2 address units inside the swizzled row
+                const uint32_t acc = kk == 0 ? acc0 : 1u;
+                if constexpr (kPair) {
+                  umma_f16_pair(tX, dA_hi + 2 * kk, dB_lo + 2 * kk, p.idesc, acc);
+                  umma_f16_pair(tX, dA_lo + 2 * kk, dB_hi + 2 * kk, p.idesc, 1u);
+                  umma_f16_pair(tY, dA_hi + 2 * kk, dB_hi + 2 * kk, p.idesc, acc);
+                } else {
+                  umma_f16(tX, dA_hi + 2 * kk, dB_lo + 2 * kk, p.idesc, acc);
+                  umma_f16(tX, dA_lo + 2 * kk, dB_hi + 2 * kk, p.idesc, 1u);
+                  umma_f16(tY, dA_hi + 2 * kk, dB_hi + 2 * kk, p.idesc, acc);
+                }
+              }
+              // the stage is free once these MMAs have read it; last tile of the unit: so is the f0 k-block
+              if constexpr (kPair) {
+                umma_commit_pair(b_empty(stage));
+                if (nt == un.n_end - 1) umma_commit_pair(a_empty(kb));
+                if (kb == p.num_kb - 1) umma_commit_pair(tfull((int)h));
+              } else {
+                umma_commit(b_empty(stage));
+                if (nt == un.n_end - 1) umma_commit(a_empty(kb));
+                if (kb == p.num_kb - 1) umma_commit(tfull((int)h));
+              }
             }
-            commit(b_empty(stage));                             // the stage is free once these MMAs have read it
-            if (nt == un.n_end - 1) commit(a_empty(kb));        // last tile of the unit: so is the f0 k-block
+            __syncwarp();
             if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
           }
-          commit(tfull((int)h));
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =============================================================== TMA producer of the resident f0 tile
+    // A separate thread: the f1 ring of warp 0 keeps prefetching across unit boundaries while this one waits for the
+    // MMAs of the previous unit's last tile to release the k-blocks of the f0 tile.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(40));
+    if (lane == 0) {
+      uint32_t ucount = 0;
+      for (int u = first; u < p.units; u += step, ++ucount) {
+        const Unit un = decode_unit(p, u);
+        const int m_tile = kPair ? un.mg * 2 + (int)rank : un.mg;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          timed_wait(a_empty(kb), (ucount & 1u) ^ 1u, 0);
+          const uint32_t dst = a_base + (uint32_t)kb * A_KB_BYTES;
+          if constexpr (kPair) {
+            const uint32_t fb = mapa_cta(a_full(kb), 0u);  // both CTAs' bytes complete on the leader's barrier
+            if (rank == 0) mbar_expect_tx(a_full(kb), 2u * A_KB_BYTES);
+            tma_load_3d_pair(dst, &maps.a_hi, fb, kb * CK, m_tile * CM, un.img);
+            tma_load_3d_pair(dst + A_PLANE_BYTES, &maps.a_lo, fb, kb * CK, m_tile * CM, un.img);
+          } else {
+            mbar_expect_tx(a_full(kb), A_KB_BYTES);
+            tma_load_3d(dst, &maps.a_hi, a_full(kb), kb * CK, m_tile * CM, un.img);
+            tma_load_3d(dst + A_PLANE_BYTES, &maps.a_lo, a_full(kb), kb * CK, m_tile * CM, un.img);
+          }
         }
       }
     }
@@ -281,6 +329,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) corr_sweep_kernel(const __grid_c
     const int q = warp & 3, h = (warp - 4) >> 2;
     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 256u;
     uint32_t tcount = 0;
+    float* thr_strip = reinterpret_cast<float*>(gen + (bars - base) + 256) + (warp - 4) * CN;  // CONF: 128 thresholds per warp
     auto release_tmem = [&]() {
       tc_fence_before();
       __syncwarp();
@@ -308,21 +357,57 @@ __global__ void __launch_bounds__(C_THREADS, 1) corr_sweep_kernel(const __grid_c
       }
       for (int nt = un.n_begin; nt < un.n_end; ++nt, ++tcount) {
         if ((int)(tcount & 1u) != h) continue;
-        mbar_wait(tfull(h), (tcount >> 1) & 1u);
-        tc_fence_after();
         const bool edge = (m_tile + 1) * CM > p.L || (nt + 1) * CN > p.S || p.mask0 != nullptr || p.mask1 != nullptr;
         const size_t cbase = (size_t)un.img * p.Sp + (size_t)nt * CN;  // padded column index of the tile's first column
 
-        uint32_t xa[32], ya[32], xb[32], yb[32];
-        // ---- block body: X/Y raw accumulators of 32 columns (lane = row)
-        auto block = [&](const uint32_t (&xr)[32], const uint32_t (&yr)[32], int b) {
+        // CONF: this tile's 128 column thresholds, one coalesced load per warp (issued before the wait on the
+        // accumulators), parked in the warp's shared-memory strip and read back as broadcasts
+        float4 thr4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (SWEEP == SWEEP_CONF) thr4 = __ldg(reinterpret_cast<const float4*>(p.colthr + cbase) + lane);
+        timed_wait(tfull(h), (tcount >> 1) & 1u, 0);
+        tc_fence_after();
+        const long long dbg_t1 = p.dbg ? clock64() : 0;
+
+        // ---- phase 1: drain.  sim (raw dot product) = Y + 2^-8 X for the tile's 128 columns of this lane's row; the
+        // accumulators go back to the MMA warp before any of the statistics math starts.
+        float t[4][32];
+        {
+          uint32_t xa[32], ya[32], xb[32], yb[32];
+          auto fold = [&](const uint32_t (&xr)[32], const uint32_t (&yr)[32], float (&dst)[32]) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j] = fmaf(__uint_as_float(xr[j]), 1.f / kSplitScale, __uint_as_float(yr[j]));
+          };
+          tmem_ld32(tbase + 0, xa);
+          tmem_ld32(tbase + 128 + 0, ya);
+          tmem_ld_wait();
+          tmem_ld32(tbase + 32, xb);
+          tmem_ld32(tbase + 128 + 32, yb);
+          fold(xa, ya, t[0]);
+          tmem_ld_wait();
+          tmem_ld32(tbase + 64, xa);
+          tmem_ld32(tbase + 128 + 64, ya);
+          fold(xb, yb, t[1]);
+          tmem_ld_wait();
+          tmem_ld32(tbase + 96, xb);
+          tmem_ld32(tbase + 128 + 96, yb);
+          fold(xa, ya, t[2]);
+          tmem_ld_wait();
+          release_tmem();
+          if (p.dbg) dbg_acc[1] += clock64() - dbg_t1;
+          fold(xb, yb, t[3]);
+        }
+        if constexpr (SWEEP == SWEEP_CONF) {
+          __syncwarp();  // the previous tile's broadcasts are done
+          *reinterpret_cast<float4*>(thr_strip + 4 * lane) = thr4;
+          __syncwarp();
+        }
+
+        // ---- phase 2: per 32-column block, from registers
+        auto block = [&](const float (&tv)[32], int b) {
           if constexpr (SWEEP == SWEEP_STATS) {
             float e[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float t = fmaf(__uint_as_float(xr[j]), 1.f / kSplitScale, __uint_as_float(yr[j]));
-              e[j] = ex2_approx(fmaf(t, p.c2, negG));
-            }
+            for (int j = 0; j < 32; ++j) e[j] = ex2_approx(fmaf(tv[j], p.c2, negG));
             if (edge) {  // warp-uniform: tail tiles and masked problems only
               const int col = nt * CN + b * 32 + lane;
               const bool cv = col < p.S && (p.mask1 == nullptr || p.mask1[(size_t)un.img * p.S + col] != 0);
@@ -340,18 +425,15 @@ __global__ void __launch_bounds__(C_THREADS, 1) corr_sweep_kernel(const __grid_c
             bfly_step<2>(e, lane);
             p.colpart[(size_t)(m_tile * 4 + q) * ((size_t)p.nb * p.Sp) + cbase + b * 32 + lane] = e[0];
           } else {
-            // thresholds of the block's 32 columns (warp-uniform addresses: one transaction per load)
             float z[32];
-            const float4* tp = reinterpret_cast<const float4*>(p.colthr + cbase + b * 32);
             const float c22 = 2.f * p.c2;
-            auto tval = [&](int j) { return fmaf(__uint_as_float(xr[j]), 1.f / kSplitScale, __uint_as_float(yr[j])); };
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 v = __ldg(tp + j4);
-              z[j4 * 4 + 0] = fmaf(tval(j4 * 4 + 0), c22, -v.x);   // log2 conf + Lr - log2(thr) + margin
-              z[j4 * 4 + 1] = fmaf(tval(j4 * 4 + 1), c22, -v.y);
-              z[j4 * 4 + 2] = fmaf(tval(j4 * 4 + 2), c22, -v.z);
-              z[j4 * 4 + 3] = fmaf(tval(j4 * 4 + 3), c22, -v.w);
+              const float4 v = *reinterpret_cast<const float4*>(thr_strip + b * 32 + j4 * 4);  // broadcast
+              z[j4 * 4 + 0] = fmaf(tv[j4 * 4 + 0], c22, -v.x);   // log2 conf + Lr - log2(thr) + margin
+              z[j4 * 4 + 1] = fmaf(tv[j4 * 4 + 1], c22, -v.y);
+              z[j4 * 4 + 2] = fmaf(tv[j4 * 4 + 2], c22, -v.z);
+              z[j4 * 4 + 3] = fmaf(tv[j4 * 4 + 3], c22, -v.w);
             }
             float m0 = max3(z[0], z[1], z[2]), m1 = max3(z[3], z[4], z[5]);
 #pragma unroll
@@ -363,7 +445,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) corr_sweep_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (z[j] > Lr) {
-                    const unsigned long long pk = conf_candidate(p, tval(j), G, R, un.img, nt * CN + b * 32 + j);
+                    const unsigned long long pk = conf_candidate(p, tv[j], G, R, un.img, nt * CN + b * 32 + j);
                     best = pk > best ? pk : best;
                   }
               }
@@ -375,31 +457,17 @@ __global__ void __launch_bounds__(C_THREADS, 1) corr_sweep_kernel(const __grid_c
                 const int col = nt * CN + b * 32 + j;
                 if (col < p.S) {
                   const bool live = Lr < INFINITY && z[j] > -INFINITY;  // masked rows / columns: exactly 0
-                  dst[j] = live ? conf_exact(p, tval(j), G, R, __ldg(p.colsum + cbase + b * 32 + j)) : 0.f;
+                  dst[j] = live ? conf_exact(p, tv[j], G, R, __ldg(p.colsum + cbase + b * 32 + j)) : 0.f;
                 }
               }
             }
           }
         };
-        // ---- software pipeline over the tile's four 32-column blocks: the next block's TMEM loads are in flight
-        // while the current one is processed
-        tmem_ld32(tbase + 0, xa);
-        tmem_ld32(tbase + 128 + 0, ya);
-        tmem_ld_wait();
-        tmem_ld32(tbase + 32, xb);
-        tmem_ld32(tbase + 128 + 32, yb);
-        block(xa, ya, 0);
-        tmem_ld_wait();
-        tmem_ld32(tbase + 64, xa);
-        tmem_ld32(tbase + 128 + 64, ya);
-        block(xb, yb, 1);
-        tmem_ld_wait();
-        tmem_ld32(tbase + 96, xb);
-        tmem_ld32(tbase + 128 + 96, yb);
-        block(xa, ya, 2);
-        tmem_ld_wait();
-        release_tmem();  // last TMEM read of the tile: the MMA warp may start the next tile of this parity
-        block(xb, yb, 3);
+        block(t[0], 0);
+        block(t[1], 1);
+        block(t[2], 2);
+        block(t[3], 3);
+        if (p.dbg) dbg_acc[2] += clock64() - dbg_t1;
       }
       // ---- unit end
       if constexpr (SWEEP == SWEEP_STATS) {
@@ -411,6 +479,13 @@ __global__ void __launch_bounds__(C_THREADS, 1) corr_sweep_kernel(const __grid_c
     }
   }
 
+  if (p.dbg != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8)) {
+    // [0..3] producer: a_empty, b_empty, -, total | [4..7] MMA: tempty, a_full, b_full, total | [8..11] / [12..15]
+    // epilogue warp 4 / 8: tfull wait, drain, tile total, kernel total
+    const int o = warp == 0 ? 0 : (warp == 1 ? 4 : (warp == 4 ? 8 : 12));
+    long long* d = p.dbg + (size_t)blockIdx.x * 16 + o;
+    d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = warp == 1 ? dbg_acc[3] : clock64() - dbg_t0;
+  }
   // ---- teardown
   tc_fence_before();
   __syncthreads();
@@ -517,8 +592,15 @@ Plan make_plan(const Ctx& ctx, int nb, int L, int S, int C) {
   pl.units = nb * pl.m_groups * pl.n_split;
   pl.b_stage_bytes = (pl.pair ? CN / 2 : CN) * CK * 2 * 2;
   const int num_kb = C / CK;
-  const int fixed = num_kb * A_KB_BYTES + 256 + 1024;
-  pl.b_stages = std::min(8, (C_SMEM_LIMIT - fixed) / pl.b_stage_bytes);
+  const int fixed = num_kb * A_KB_BYTES + 256 /*barriers*/ + 8 * CN * 4 /*threshold strips*/ + 1024 /*alignment*/;
+  // three stages: measured faster than 4 or 5 (835 vs 868 us per 32 pairs for the stats sweep, tensor pipe 76.7 vs 70.3 %);
+  // the MMA warp never waits longer for f1 with the shorter ring, and fewer bulk copies are in flight beside the operand reads
+  pl.b_stages = std::min(3, (C_SMEM_LIMIT - fixed) / pl.b_stage_bytes);
+  {
+    static int forced = -1;  // measurement knob
+    if (forced < 0) { const char* e = getenv("GIMB_CORR_STAGES"); forced = e ? atoi(e) : 0; }
+    if (forced > 0) pl.b_stages = std::min((C_SMEM_LIMIT - fixed) / pl.b_stage_bytes, forced);
+  }
   pl.smem = fixed + pl.b_stages * pl.b_stage_bytes;
   return pl;
 }
@@ -590,11 +672,33 @@ int corr_sweeps(Ctx& ctx, const CorrSweep& c) {
   GIMB_SMEM_OPTIN((corr_sweep_kernel<SWEEP_STATS, true>), C_SMEM_LIMIT);
   GIMB_SMEM_OPTIN((corr_sweep_kernel<SWEEP_CONF, true>), C_SMEM_LIMIT);
 
+  static int dbg_on = -1;
+  if (dbg_on < 0) { const char* e = getenv("GIMB_CORR_DEBUG"); dbg_on = (e && atoi(e) != 0) ? 1 : 0; }
+  long long* dbg = nullptr;
+  if (dbg_on) {
+    GIMB_CUDA(cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long)));
+    GIMB_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(long long), ctx.stream));
+    p.dbg = dbg;
+  }
+  auto dump_dbg = [&](const char* what) {
+    if (!dbg) return;
+    std::vector<long long> h((size_t)grid * 16);
+    cudaStreamSynchronize(ctx.stream);
+    cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double avg[16] = {0};
+    for (int g = 0; g < grid; ++g) for (int k = 0; k < 16; ++k) avg[k] += (double)h[(size_t)g * 16 + k] / grid;
+    fprintf(stderr, "[corr dbg %s] units %d tiles/unit %d grid %d | producer a_empty %.0f b_empty %.0f total %.0f | mma tempty %.0f a_full %.0f "
+            "b_full %.0f (+ first tile of a unit %.0f) | epi4 tfull %.0f drain %.0f tiles %.0f total %.0f | epi8 tfull %.0f drain %.0f tiles %.0f total %.0f\n",
+            what, pl.units, pl.tiles_per_unit, grid, avg[0], avg[1], avg[3], avg[4], avg[5], avg[6], avg[7], avg[8], avg[9], avg[10], avg[11],
+            avg[12], avg[13], avg[14], avg[15]);
+    cudaMemset(dbg, 0, h.size() * sizeof(long long));
+  };
   // ---- sweep 1
   if (pl.pair) GIMB_CUDA(cudaLaunchKernelEx(&lcfg, corr_sweep_kernel<SWEEP_STATS, true>, maps, p));
   else GIMB_CUDA(cudaLaunchKernelEx(&lcfg, corr_sweep_kernel<SWEEP_STATS, false>, maps, p));
   GIMB_LAUNCH_CHECK();
   ctx.mark("corr_stats");
+  dump_dbg("stats");
   // ---- merge
   const float thr_log2 = c.thr > 0.f ? log2f(c.thr) - 1e-3f : -INFINITY;
   const size_t nrow = (size_t)c.N * p.Lp, ncol = (size_t)c.N * p.Sp;
@@ -612,6 +716,8 @@ int corr_sweeps(Ctx& ctx, const CorrSweep& c) {
   else GIMB_CUDA(cudaLaunchKernelEx(&lcfg, corr_sweep_kernel<SWEEP_CONF, false>, maps, p));
   GIMB_LAUNCH_CHECK();
   ctx.mark("corr_conf");
+  dump_dbg("conf");
+  if (dbg) cudaFree(dbg);
   ctx.launches += 5;
   return 0;
 }
