@@ -48,6 +48,7 @@ EXPORTS = {
 
 # libgimb200_test.so = the product library + the layer-level test / measurement hooks (include/gimb200_test.h)
 TEST_LIB_PATH = os.path.join(HERE, "libgimb200_test.so")
+TEST_LIB_PATH = os.environ.get("GIMB_TEST_LIB", TEST_LIB_PATH)  # measurement only: A/B two builds
 TEST_EXPORTS = {
     "gimb_bench_layer": (c_int, [c_int] * 11 + [POINTER(c_float), c_void_p]),
     "gimb_probe_tma": (c_int, [c_int, c_int, POINTER(c_float), c_void_p]),

