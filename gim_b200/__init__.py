@@ -1,4 +1,4 @@
-"""gim_b200 - B200 (sm_100a) native gim_loftr dense image-pair matcher behind the reference's module API.
+"""gim_b200 - B200 (sm_100a) native gim_loftr / gim_dkm dense image-pair matchers behind the reference's module API.
 
     from gim_b200 import LoFTR, load_default_weights
     model = LoFTR(get_default_config()); model.load_state_dict(load_default_weights()); model.eval().cuda()
@@ -17,4 +17,7 @@ def __getattr__(name):
     if name == "LoFTR":
         from .loftr import LoFTR
         return LoFTR
+    if name in ("DKMv3", "HlocDKM"):
+        from . import dkm
+        return getattr(dkm, name)
     raise AttributeError(name)

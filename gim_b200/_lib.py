@@ -39,11 +39,24 @@ EXPORTS = {
                                         POINTER(LoftrOut), POINTER(LoftrOut), POINTER(c_int64), POINTER(c_uint64),
                                         POINTER(c_uint64), c_void_p]),
     "gimb_loftr_host_staging_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "gimb_loftr_host_u8_staging_bytes": (c_int, [c_int] * 10 + [POINTER(c_size_t)]),
+    "gimb_loftr_forward_host_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                           c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_size_t,
+                                           POINTER(LoftrOut), POINTER(LoftrOut), POINTER(c_int64), POINTER(c_uint64),
+                                           POINTER(c_uint64), c_void_p]),
     "gimb_loftr_launch_count": (c_uint64, [c_void_p]),
     "gimb_loftr_corr_fallbacks": (c_uint64, [c_void_p]),
     "gimb_loftr_set_profiling": (c_int, [c_void_p, c_int]),
     "gimb_loftr_set_engine": (c_int, [c_void_p, c_int]),
     "gimb_loftr_last_profile": (c_int, [c_void_p, POINTER(c_char_p), POINTER(c_float), POINTER(c_int)]),
+    # ---- gim_dkm (include/gimb200.h, csrc/dkm_api.cu)
+    "gimb_dkm_create": (c_int, [c_char_p, c_size_t, c_int, POINTER(c_void_p)]),
+    "gimb_dkm_destroy": (None, [c_void_p]),
+    "gimb_dkm_set_engine": (c_int, [c_void_p, c_int]),
+    "gimb_dkm_launch_count": (c_uint64, [c_void_p]),
+    "gimb_dkm_workspace_bytes": (c_int, [c_void_p] + [c_int] * 9 + [POINTER(c_size_t)]),
+    "gimb_dkm_match": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 # libgimb200_test.so = the product library + the layer-level test / measurement hooks (include/gimb200_test.h)

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgimb200.so")
 TEST_LIB = os.path.join(HERE, "libgimb200_test.so")  # product objects + csrc/test_hooks.cu (include/gimb200_test.h)
-SOURCES = ["common.cu", "engine.cu", "conv_simt.cu", "transformer.cu", "coarse_match.cu", "fine.cu", "umma_gemm.cu", "corr_sweep.cu", "loftr_api.cu"]
+SOURCES = ["common.cu", "engine.cu", "conv_simt.cu", "transformer.cu", "coarse_match.cu", "fine.cu", "umma_gemm.cu", "corr_sweep.cu", "loftr_api.cu", "dkm_kernels.cu", "dkm_api.cu"]
 TEST_SOURCES = ["test_hooks.cu", "probe_mma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -437,6 +437,26 @@ int check_shapes(int n, int h0, int w0, int h1, int w1) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- GPU pre-processing: what the ZEB loader does on the host per image (datasets/utils.py:112-124) -
+// uint8 HWC -> float / 255 -> CHW, zero padding at the bottom / right, and the padding mask at 1/8 resolution
+// (datasets/kitti/kitti.py:115-123: nearest-neighbour 1/8 of the full-resolution mask = mask[8y, 8x]).
+__global__ void u8_to_nchw_kernel(const uint8_t* __restrict__ src, int n, int ih, int iw, float* __restrict__ dst, int H, int W) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)n * 3 * H * W;
+  if (idx >= total) return;
+  const int x = (int)(idx % W), y = (int)((idx / W) % H), c = (int)((idx / ((long long)W * H)) % 3);
+  const long long b = idx / ((long long)3 * H * W);
+  float v = 0.f;
+  if (y < ih && x < iw) v = __fdiv_rn((float)src[((b * ih + y) * iw + x) * 3 + c], 255.f);
+  dst[idx] = v;
+}
+__global__ void pad_mask_kernel(uint8_t* __restrict__ mask, int n, int hc, int wc, int ih, int iw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * hc * wc) return;
+  const int x = idx % wc, y = (idx / wc) % hc;
+  mask[idx] = (8 * y < ih && 8 * x < iw) ? 1 : 0;
+}
+
 }  // namespace
 }  // namespace gimb
 
@@ -599,6 +619,94 @@ int gimb_loftr_forward_host(gimb_loftr* h, const float* color0, const float* col
   GIMB_TRY(gimb_loftr_forward(h, (const float*)d_c0, (const float*)d_c1, (const uint8_t*)d_m0, (const uint8_t*)d_m1,
                               (const float*)d_s0, (const float*)d_s1, n, h0, w0, h1, w1, workspace, workspace_bytes,
                               dev_out, nullptr, m_out, stream));
+  const int64_t M = *m_out;
+  GIMB_CHECK(M <= host_out->capacity, "host_out capacity %lld < M = %lld", (long long)host_out->capacity, (long long)M);
+  uint64_t down = sizeof(int64_t);
+  auto pull = [&](void* dst, const void* src, size_t bytes) -> int {
+    if (!dst || bytes == 0) return 0;
+    GIMB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    down += bytes;
+    return 0;
+  };
+  GIMB_TRY(pull(host_out->b_ids, dev_out->b_ids, M * 8));
+  GIMB_TRY(pull(host_out->i_ids, dev_out->i_ids, M * 8));
+  GIMB_TRY(pull(host_out->j_ids, dev_out->j_ids, M * 8));
+  GIMB_TRY(pull(host_out->mconf, dev_out->mconf, M * 4));
+  GIMB_TRY(pull(host_out->mkpts0_c, dev_out->mkpts0_c, M * 8));
+  GIMB_TRY(pull(host_out->mkpts1_c, dev_out->mkpts1_c, M * 8));
+  GIMB_TRY(pull(host_out->mkpts0_f, dev_out->mkpts0_f, M * 8));
+  GIMB_TRY(pull(host_out->mkpts1_f, dev_out->mkpts1_f, M * 8));
+  GIMB_TRY(pull(host_out->expec_f, dev_out->expec_f, M * 12));
+  GIMB_CUDA(cudaStreamSynchronize(st));
+  if (h2d_bytes) *h2d_bytes = up;
+  if (d2h_bytes) *d2h_bytes = down;
+  return 0;
+}
+
+int gimb_loftr_host_u8_staging_bytes(int n, int ih0, int iw0, int ih1, int iw1, int h0, int w0, int h1, int w1, int with_scale,
+                                     size_t* bytes) {
+  GIMB_CHECK(bytes, "null argument");
+  GIMB_TRY(check_shapes(n, h0, w0, h1, w1));
+  GIMB_CHECK(ih0 > 0 && iw0 > 0 && ih1 > 0 && iw1 > 0 && ih0 <= h0 && iw0 <= w0 && ih1 <= h1 && iw1 <= w1,
+             "u8 images must fit inside the padded sizes");
+  size_t b = 256;
+  b += align_up((size_t)n * ih0 * iw0 * 3, 256) + align_up((size_t)n * ih1 * iw1 * 3, 256);
+  b += align_up((size_t)n * 3 * h0 * w0 * 4, 256) + align_up((size_t)n * 3 * h1 * w1 * 4, 256);
+  b += align_up((size_t)n * (h0 / 8) * (w0 / 8), 256) + align_up((size_t)n * (h1 / 8) * (w1 / 8), 256);
+  if (with_scale) b += 2 * align_up((size_t)n * 2 * 4, 256);
+  *bytes = b + 256;
+  return 0;
+}
+
+int gimb_loftr_forward_host_u8(gimb_loftr* h, const uint8_t* img0, int ih0, int iw0, const uint8_t* img1, int ih1, int iw1,
+                               const float* scale0, const float* scale1, int n, int h0, int w0, int h1, int w1, void* dev_inputs,
+                               size_t dev_inputs_bytes, void* workspace, size_t workspace_bytes, const gimb_loftr_out* dev_out,
+                               const gimb_loftr_out* host_out, int64_t* m_out, uint64_t* h2d_bytes, uint64_t* d2h_bytes,
+                               void* stream) {
+  GIMB_CHECK(h && img0 && img1 && dev_inputs && dev_out && host_out && m_out, "gimb_loftr_forward_host_u8: null argument");
+  GIMB_CHECK((scale0 == nullptr) == (scale1 == nullptr), "scale0/scale1 go together");
+  size_t need = 0;
+  GIMB_TRY(gimb_loftr_host_u8_staging_bytes(n, ih0, iw0, ih1, iw1, h0, w0, h1, w1, scale0 != nullptr, &need));
+  GIMB_CHECK(dev_inputs_bytes >= need, "dev_inputs too small: %zu < %zu", dev_inputs_bytes, need);
+  DeviceGuard guard(h->device);
+  GIMB_CHECK(guard.ok, "cudaSetDevice(%d) failed", h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = (char*)(((uintptr_t)dev_inputs + 255) / 256 * 256);
+  uint64_t up = 0;
+  auto carve = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
+  const size_t b0 = (size_t)n * ih0 * iw0 * 3, b1 = (size_t)n * ih1 * iw1 * 3;
+  uint8_t* d_u0 = (uint8_t*)carve(b0);
+  uint8_t* d_u1 = (uint8_t*)carve(b1);
+  float* d_c0 = (float*)carve((size_t)n * 3 * h0 * w0 * 4);
+  float* d_c1 = (float*)carve((size_t)n * 3 * h1 * w1 * 4);
+  const bool padded = ih0 != h0 || iw0 != w0 || ih1 != h1 || iw1 != w1;  // the loader returns a mask only when it pads
+  uint8_t* d_m0 = (uint8_t*)carve((size_t)n * (h0 / 8) * (w0 / 8));
+  uint8_t* d_m1 = (uint8_t*)carve((size_t)n * (h1 / 8) * (w1 / 8));
+  GIMB_CUDA(cudaMemcpyAsync(d_u0, img0, b0, cudaMemcpyHostToDevice, st));
+  GIMB_CUDA(cudaMemcpyAsync(d_u1, img1, b1, cudaMemcpyHostToDevice, st));
+  up += b0 + b1;
+  const float *d_s0 = nullptr, *d_s1 = nullptr;
+  if (scale0) {
+    float* s0 = (float*)carve((size_t)n * 8);
+    float* s1 = (float*)carve((size_t)n * 8);
+    GIMB_CUDA(cudaMemcpyAsync(s0, scale0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    GIMB_CUDA(cudaMemcpyAsync(s1, scale1, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    d_s0 = s0; d_s1 = s1;
+    up += (uint64_t)n * 16;
+  }
+  {
+    const long long t0 = (long long)n * 3 * h0 * w0, t1 = (long long)n * 3 * h1 * w1;
+    u8_to_nchw_kernel<<<(unsigned)((t0 + 255) / 256), 256, 0, st>>>(d_u0, n, ih0, iw0, d_c0, h0, w0);
+    u8_to_nchw_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, st>>>(d_u1, n, ih1, iw1, d_c1, h1, w1);
+    if (padded) {
+      pad_mask_kernel<<<(n * (h0 / 8) * (w0 / 8) + 255) / 256, 256, 0, st>>>(d_m0, n, h0 / 8, w0 / 8, ih0, iw0);
+      pad_mask_kernel<<<(n * (h1 / 8) * (w1 / 8) + 255) / 256, 256, 0, st>>>(d_m1, n, h1 / 8, w1 / 8, ih1, iw1);
+    }
+    GIMB_LAUNCH_CHECK();
+    h->launches += padded ? 4 : 2;
+  }
+  GIMB_TRY(gimb_loftr_forward(h, d_c0, d_c1, padded ? d_m0 : nullptr, padded ? d_m1 : nullptr, d_s0, d_s1, n, h0, w0, h1, w1,
+                              workspace, workspace_bytes, dev_out, nullptr, m_out, stream));
   const int64_t M = *m_out;
   GIMB_CHECK(M <= host_out->capacity, "host_out capacity %lld < M = %lld", (long long)host_out->capacity, (long long)M);
   uint64_t down = sizeof(int64_t);

@@ -319,6 +319,68 @@ class LoFTR(nn.Module):
         if taps:
             data["_taps"] = {k: (v[:M] if k.startswith("fine_win") else v) for k, v in tap_tensors.items()}
 
+    @torch.no_grad()
+    def forward_u8(self, data):
+        """GPU pre-processing entry (`gimb_loftr_forward_host_u8`): `data['color0_u8'|'color1_u8']` are
+        CPU uint8 RGB tensors [N, h, w, 3] as cv2 delivers them (after the loader's cv2.resize, datasets/utils.py:108);
+        the float conversion (/255), HWC -> CHW, the zero padding to `data['pad0'|'pad1']` = (H, W) (default: the image
+        size, which must then be a multiple of 8) and the 1/8 padding masks happen on the device.  Optional
+        `scale0/scale1` [N, 2].  Results come back as CPU tensors under the same keys as forward()."""
+        self._ensure_handle()
+        lib = _lib.load()
+        dev = self._device()
+        u0, u1 = data["color0_u8"], data["color1_u8"]
+        if u0.dtype != torch.uint8 or u1.dtype != torch.uint8 or u0.dim() != 4 or u1.dim() != 4 or u0.shape[3] != 3 or \
+                u1.shape[3] != 3 or u0.shape[0] != u1.shape[0] or u0.device.type != "cpu" or u1.device.type != "cpu":
+            raise RuntimeError("color0_u8 / color1_u8 must be CPU uint8 tensors [N, h, w, 3] with equal N")
+        u0, u1 = u0.contiguous(), u1.contiguous()
+        n, ih0, iw0, _ = u0.shape
+        _, ih1, iw1, _ = u1.shape
+        h0, w0 = data.get("pad0", (ih0, iw0))
+        h1, w1 = data.get("pad1", (ih1, iw1))
+        if any(v % 8 for v in (h0, w0, h1, w1)):
+            raise RuntimeError(f"padded image sizes must be multiples of 8, got {h0}x{w0}, {h1}x{w1}")
+        has_scale = "scale0" in data
+        s0 = s1 = None
+        if has_scale:
+            s0, s1 = data["scale0"].to(torch.float32).contiguous().cpu(), data["scale1"].to(torch.float32).contiguous().cpu()
+        hc0, wc0, hc1, wc1 = h0 // 8, w0 // 8, h1 // 8, w1 // 8
+        self._ensure_pe(hc0, wc0)
+        self._ensure_pe(hc1, wc1)
+        with torch.cuda.device(dev):
+            ws = self._ensure_workspace(n, h0, w0, h1, w1, dev)
+            cap = n * min(hc0 * wc0, hc1 * wc1)
+            outs = self._alloc_outputs(cap, dev)
+            o = self._out_struct(cap, outs)
+            need = ctypes.c_size_t()
+            _lib.check(lib.gimb_loftr_host_u8_staging_bytes(n, ih0, iw0, ih1, iw1, h0, w0, h1, w1, int(has_scale), ctypes.byref(need)))
+            if self._staging is None or self._staging.numel() < need.value or self._staging.device != dev:
+                self._staging = torch.empty(need.value, dtype=torch.uint8, device=dev)
+            if self._host_out is None or self._host_out["b_ids"].shape[0] < cap:
+                self._host_out = self._alloc_outputs(cap, torch.device("cpu"), pin=True)
+            houts = self._host_out
+            ho = self._out_struct(houts["b_ids"].shape[0], houts)
+            up, down, m_out = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int64()
+            ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+            _lib.check(lib.gimb_loftr_forward_host_u8(self._handle, u0.data_ptr(), ih0, iw0, u1.data_ptr(), ih1, iw1, ptr(s0), ptr(s1),
+                                                      n, h0, w0, h1, w1, self._staging.data_ptr(), self._staging.numel(),
+                                                      ws.data_ptr(), ws.numel(), ctypes.byref(o), ctypes.byref(ho),
+                                                      ctypes.byref(m_out), ctypes.byref(up), ctypes.byref(down),
+                                                      torch.cuda.current_stream(dev).cuda_stream))
+            M = m_out.value
+            self.last_h2d_bytes, self.last_d2h_bytes = up.value, down.value
+            res = {k: v[:M].clone() for k, v in houts.items()}
+        data.update({
+            "bs": n, "hw0_i": torch.Size((h0, w0)), "hw1_i": torch.Size((h1, w1)),
+            "hw0_c": torch.Size((hc0, wc0)), "hw1_c": torch.Size((hc1, wc1)),
+            "hw0_f": torch.Size((h0 // 2, w0 // 2)), "hw1_f": torch.Size((h1 // 2, w1 // 2)),
+            "b_ids": res["b_ids"], "i_ids": res["i_ids"], "j_ids": res["j_ids"],
+            "gt_mask": res["mconf"] == 0, "m_bids": res["b_ids"],
+            "mkpts0_c": res["mkpts0_c"], "mkpts1_c": res["mkpts1_c"], "mconf": res["mconf"],
+            "W": int(self.config["fine_window_size"]), "expec_f": res["expec_f"],
+            "mkpts0_f": res["mkpts0_f"], "mkpts1_f": res["mkpts1_f"],
+        })
+
     @staticmethod
     def _alloc_outputs(cap, dev, pin=False):
         kw = dict(device=dev)

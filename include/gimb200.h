@@ -138,6 +138,21 @@ int gimb_loftr_forward_host(gimb_loftr* h, const float* color0, const float* col
 int gimb_loftr_host_staging_bytes(int n, int h0, int w0, int h1, int w1, int with_mask,
                                   int with_scale, size_t* bytes);
 
+/* GPU pre-processing entry.  Replaces, per image, the host work of the ZEB loader after cv2.resize
+ * (datasets/utils.py:112-124: zero padding at the bottom / right, float / 255, HWC -> CHW, padding mask) and of
+ * demo.py:166-176: img0 [n, ih0, iw0, 3] / img1 [n, ih1, iw1, 3] are uint8 RGB HWC HOST buffers; they are copied as
+ * bytes (a quarter of the fp32 traffic), converted and zero-padded to (h0, w0) / (h1, w1) on the device, and when any
+ * padding happens mask0 / mask1 are generated at 1/8 resolution exactly like datasets/kitti/kitti.py:115-123.
+ * Everything else as gimb_loftr_forward_host. */
+int gimb_loftr_host_u8_staging_bytes(int n, int ih0, int iw0, int ih1, int iw1, int h0, int w0, int h1,
+                                     int w1, int with_scale, size_t* bytes);
+int gimb_loftr_forward_host_u8(gimb_loftr* h, const uint8_t* img0, int ih0, int iw0, const uint8_t* img1,
+                               int ih1, int iw1, const float* scale0, const float* scale1, int n, int h0,
+                               int w0, int h1, int w1, void* dev_inputs, size_t dev_inputs_bytes,
+                               void* workspace, size_t workspace_bytes, const gimb_loftr_out* dev_out,
+                               const gimb_loftr_out* host_out, int64_t* m_out, uint64_t* h2d_bytes,
+                               uint64_t* d2h_bytes, void* stream);
+
 /* Number of kernels this library launched on behalf of handle `h` since creation (for bench.py's
  * `gpu_launches`), and the per-stage device time of the last forward when profiling is enabled. */
 uint64_t gimb_loftr_launch_count(gimb_loftr* h);
@@ -151,6 +166,43 @@ int gimb_loftr_set_engine(gimb_loftr* h, int engine);
 int gimb_loftr_set_profiling(gimb_loftr* h, int enabled);
 /* names/ms arrays of length *n_stages (<= 32) for the last profiled forward. */
 int gimb_loftr_last_profile(gimb_loftr* h, const char** names, float* ms, int* n_stages);
+
+/* =================================================================================================
+ * gim_dkm (DKMv3 dense matcher)
+ * Replaces: networks/dkm/models/model_zoo/DKMv3.py:5-145 (construction) and
+ * RegressionMatcher.match with symmetric = True, batched = False (networks/dkm/models/dkm.py:655-752).
+ * The packed blob comes from gim_b200/dkm.py::pack_dkm_blob (same container layout as above).           */
+typedef struct gimb_dkm gimb_dkm;
+
+/* optional debug taps (device pointers, channels-last; index = log2(scale)): pyramid levels of pass 1, GP outputs,
+ * flow [2, h/s, w/s, 2] / certainty [2, h/s, w/s] after every scale of pass 1 and of the upsample pass */
+typedef struct {
+  float* enc[6];
+  float* gp32;
+  float* gp16;
+  float* flow[6];
+  float* cert[6];
+  float* flow_up[6];
+  float* cert_up[6];
+  float* dfn_flow16;  /* [2, h/16, w/16, 2] flow out of the DFN at scale 16, before its ConvRefiner */
+  float* refiner_in16; /* [2, h/16, w/16, 1377] cat(x, x_hat, displacement embedding, local correlation) */
+} gimb_dkm_taps;
+
+int gimb_dkm_create(const void* blob, size_t nbytes, int device, gimb_dkm** out);
+void gimb_dkm_destroy(gimb_dkm* h);
+int gimb_dkm_set_engine(gimb_dkm* h, int engine);
+uint64_t gimb_dkm_launch_count(gimb_dkm* h);
+/* Bytes of device workspace one match() call needs.  im1 is [3, H1, W1], im2 [3, H2, W2]; (h_resized, w_resized) are the
+ * caller-overwritable attributes of the reference object (trainer/lightning.py:32-37), multiples of 32; when
+ * upsample_preds != 0 the second pass runs at (up_h, up_w) (multiples of 8). */
+int gimb_dkm_workspace_bytes(gimb_dkm* h, int H1, int W1, int H2, int W2, int h_resized, int w_resized,
+                             int upsample_preds, int up_h, int up_w, size_t* bytes);
+/* match(): DEVICE fp32 NCHW images in [0, 1]; outputs warp [Hout, 2*Wout, 4] and certainty [Hout, 2*Wout] with
+ * (Hout, Wout) = upsample_preds ? (up_h, up_w) : (h_resized, w_resized) - the tensors RegressionMatcher.match returns. */
+int gimb_dkm_match(gimb_dkm* h, const float* im1, int H1, int W1, const float* im2, int H2, int W2,
+                   int h_resized, int w_resized, int upsample_preds, int up_h, int up_w, void* workspace,
+                   size_t workspace_bytes, float* warp, float* certainty, const gimb_dkm_taps* taps,
+                   void* stream);
 
 #ifdef __cplusplus
 }

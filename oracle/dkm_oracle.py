@@ -115,7 +115,7 @@ def local_correlation(f0, f1, r, flow):
     return torch.einsum("bchw, bchwk -> bkhw", f0, wf) / (c ** 0.5)
 
 
-def conv_refiner(x, y, flow, sd, key, radius):
+def conv_refiner(x, y, flow, sd, key, radius, taps=None):
     """ConvRefiner.forward (models/dkm.py:75-123) as configured by model_zoo/DKMv3.py:52-111
     (displacement_emb='linear', corr_in_other=True, depthwise 5x5 blocks)."""
     p = f"decoder.conv_refiner.{key}."
@@ -127,6 +127,8 @@ def conv_refiner(x, y, flow, sd, key, radius):
     if radius:
         parts.append(local_correlation(x, y, radius, flow))
     d = torch.cat(parts, dim=1)
+    if taps is not None and f"refiner_in{key}" not in taps:
+        taps[f"refiner_in{key}"] = d
 
     def block(d, pre):
         d = _conv(d, sd, pre + ".0", padding=2, groups=d.shape[1])  # depthwise (dw=True), out_dim a multiple of in_dim
@@ -170,7 +172,7 @@ def decoder(f1, f2, sd, upsample=False, dense_flow=None, dense_certainty=None, t
             dense_flow, dense_certainty, old = dfn(new, a, old, sd, s)
             if taps is not None:
                 taps[f"dfn_flow{s}"] = dense_flow
-        dc, disp = conv_refiner(a, c, dense_flow, sd, s, REFINER_RADIUS[s]) if s != "32" else (None, None)
+        dc, disp = conv_refiner(a, c, dense_flow, sd, s, REFINER_RADIUS[s], taps) if s != "32" else (None, None)
         if s != "32":
             dense_flow = torch.stack((dense_flow[:, 0] + ins * disp[:, 0] / (4 * w), dense_flow[:, 1] + ins * disp[:, 1] / (4 * h)), dim=1)
             dense_certainty = dense_certainty + dc

@@ -171,3 +171,33 @@ def test_batch_consistency_and_fine_chunking(model):
     # ordered by (b, i) like torch.where
     key = big["b_ids"] * 4800 + big["i_ids"]
     assert bool((key[1:] > key[:-1]).all())
+
+
+def test_u8_entry_matches_float_entry_and_masks(model):
+    """uint8 HWC host images -> device /255, CHW, zero padding and 1/8 padding masks; the same matches as
+    the float entry fed with the host-side pre-processing of the reference loader (datasets/utils.py:112-124)."""
+    import numpy as np
+    z = np.load("tests/golden/small_b2_240x320.npz")
+    u0 = torch.from_numpy(z["color0_u8"]).permute(0, 2, 3, 1).contiguous()  # [N, h, w, 3] uint8
+    u1 = torch.from_numpy(z["color1_u8"]).permute(0, 2, 3, 1).contiguous()
+    n, h, w, _ = u0.shape
+    # (a) no padding: identical to the golden
+    d = {"color0_u8": u0, "color1_u8": u1}
+    model.forward_u8(d)
+    _, gold = load_case("small_b2_240x320")
+    assert_matches_equal(d, gold, what="u8 entry vs golden: ")
+    assert model.last_h2d_bytes == 2 * n * h * w * 3
+    # (b) padded to a square with masks: equals the float entry on host-padded inputs + host-made masks
+    P = 320
+    d2 = {"color0_u8": u0, "color1_u8": u1, "pad0": (P, P), "pad1": (P, P)}
+    model.forward_u8(d2)
+    c0 = torch.zeros(n, 3, P, P); c1 = torch.zeros(n, 3, P, P)
+    c0[:, :, :h, :w] = u0.permute(0, 3, 1, 2).float() / 255
+    c1[:, :, :h, :w] = u1.permute(0, 3, 1, 2).float() / 255
+    m = torch.zeros(n, P // 8, P // 8, dtype=torch.bool); m[:, : h // 8, : w // 8] = True
+    ref = to_cuda({"color0": c0, "color1": c1, "image0": c0, "image1": c1, "mask0": m, "mask1": m.clone()})
+    model(ref)
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(d2[k], ref[k].cpu()), k
+    assert (d2["mkpts1_f"] - ref["mkpts1_f"].cpu()).abs().max().item() < 1e-4
+    assert d2["b_ids"].numel() > 100
