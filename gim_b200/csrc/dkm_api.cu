@@ -278,7 +278,7 @@ int gp_regression(Fwd& F, gimb_dkm* m, int si, const ActT& fx, const ActT& fy, i
 
 // ConvRefiner.forward (dkm.py:75-123): returns the head [B, hw, 8] = (certainty, dx, dy, 0...) in `head`
 int conv_refiner(Fwd& F, const Refiner& r, const float* x, const float* y, int ld_xy, int B, int h, int w, const float* flow, float* head,
-                 float* tap_in = nullptr) {
+                 float* tap_in = nullptr, float* tap_dw = nullptr, float* tap_pw = nullptr, float* tap_out = nullptr) {
   Ctx& ctx = F.ctx;
   Arena& A = ctx.arena;
   size_t mark = A.mark();
@@ -303,8 +303,11 @@ int conv_refiner(Fwd& F, const Refiner& r, const float* x, const float* y, int l
     } else {
       GIMB_TRY(dkm_depthwise5x5(ctx, cur, B, h, w, cur_c, cur_ld, mult, r.dw_w[k], r.dw_s[k], r.dw_b[k], ta.f32, r.hidden, nullptr));
     }
+    if (k == 0 && tap_dw && !ctx.dry && F.tc()) GIMB_TRY(planes_to_f32(ctx, ta.sp, (int64_t)P, r.hidden, tap_dw, r.hidden));
     ActT o = act_f32(tb, r.hidden, F.tc() ? ldh : r.hidden);
     GIMB_TRY(run_conv(F, r.pw[k], ta, B, h, w, 1, ACT_NONE, nullptr, o));
+    if (k == 0 && tap_pw && !ctx.dry) GIMB_TRY(dkm_copy_channels(ctx, tb, (int64_t)P, r.hidden, o.pitch(), tap_pw, r.hidden, 0));
+    if (k == 8 && tap_out && !ctx.dry) GIMB_TRY(dkm_copy_channels(ctx, tb, (int64_t)P, r.hidden, o.pitch(), tap_out, r.hidden, 0));
     cur = tb; cur_c = r.hidden; cur_ld = o.pitch();
   }
   GIMB_TRY(conv_f32(F, r.out, cur, cur_ld, B, h, w, ACT_NONE, nullptr, head, 8));
@@ -391,7 +394,8 @@ int decoder(Fwd& F, gimb_dkm* m, const Pyramid& py, const Pyramid& sw, bool upsa
       if (s <= 4) {  // conv_refiner["16"]
         if (taps && taps->dfn_flow16 && !ctx.dry)
           GIMB_CUDA(cudaMemcpyAsync(taps->dfn_flow16, flow, P * 2 * sizeof(float), cudaMemcpyDeviceToDevice, ctx.stream));
-        GIMB_TRY(conv_refiner(F, m->ref[0], p1.f32, p2.f32, 512, B, hs, ws, flow, head, taps ? taps->refiner_in16 : nullptr));
+        GIMB_TRY(conv_refiner(F, m->ref[0], p1.f32, p2.f32, 512, B, hs, ws, flow, head, taps ? taps->refiner_in16 : nullptr,
+                              taps ? taps->refiner_dw16 : nullptr, taps ? taps->refiner_pw16 : nullptr, taps ? taps->refiner_out16 : nullptr));
         GIMB_TRY(dkm_apply_delta(ctx, flow, cert, true, head, 8, B, hs, ws, (float)ins, W, H));
       }
       if (s == 4 && !ctx.dry)

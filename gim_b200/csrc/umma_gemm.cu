@@ -1033,7 +1033,9 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
   p.mode = g.mode;
   p.N = g.N;
   p.n_tiles = cdiv(g.N, 256);
-  p.bn = cdiv(cdiv(g.N, p.n_tiles), 16) * 16;
+  // several n tiles: whole 32-column epilogue blocks per tile (a block that straddles the tile edge would store the next
+  // tile's columns); a single tile only needs the MMA granularity of 16
+  p.bn = p.n_tiles > 1 ? cdiv(cdiv(g.N, p.n_tiles), 32) * 32 : cdiv(g.N, 16) * 16;
   p.KH = g.KH; p.KW = g.KW; p.stride = g.stride; p.pad = g.pad;
   p.K1 = g.K1;
   // ---- shared-memory plan.  Epilogue staging first (TMA epilogue: 4 KB per staged tensor per epilogue warp), then the

@@ -107,7 +107,8 @@ def pack_dkm_blob(state_dict):
 class _Taps(ctypes.Structure):
     _fields_ = [("enc", ctypes.c_void_p * 6), ("gp32", ctypes.c_void_p), ("gp16", ctypes.c_void_p), ("flow", ctypes.c_void_p * 6),
                 ("cert", ctypes.c_void_p * 6), ("flow_up", ctypes.c_void_p * 6), ("cert_up", ctypes.c_void_p * 6),
-                ("dfn_flow16", ctypes.c_void_p), ("refiner_in16", ctypes.c_void_p)]
+                ("dfn_flow16", ctypes.c_void_p), ("refiner_in16", ctypes.c_void_p), ("refiner_dw16", ctypes.c_void_p),
+                ("refiner_pw16", ctypes.c_void_p), ("refiner_out16", ctypes.c_void_p)]
 
 
 class RegressionMatcher(DKMParams):
@@ -203,7 +204,7 @@ class RegressionMatcher(DKMParams):
             if self.debug_taps:
                 taps = _Taps()
                 for name in self.debug_taps:
-                    if name in ("dfn_flow16", "refiner_in16"):
+                    if name in ("dfn_flow16", "refiner_in16", "refiner_dw16", "refiner_pw16", "refiner_out16"):
                         t = torch.zeros(2, h // 16, w // 16, 2 if name == "dfn_flow16" else 1377, device=im1.device)
                         setattr(taps, name, t.data_ptr())
                         self.last_taps[name] = t

@@ -186,6 +186,9 @@ typedef struct {
   float* cert_up[6];
   float* dfn_flow16;  /* [2, h/16, w/16, 2] flow out of the DFN at scale 16, before its ConvRefiner */
   float* refiner_in16; /* [2, h/16, w/16, 1377] cat(x, x_hat, displacement embedding, local correlation) */
+  float* refiner_dw16; /* [2, h/16, w/16, 1377] block1: depthwise 5x5 + BN + ReLU */
+  float* refiner_pw16; /* [2, h/16, w/16, 1377] block1: pointwise output */
+  float* refiner_out16; /* [2, h/16, w/16, 1377] after the 8 hidden blocks (input of out_conv) */
 } gimb_dkm_taps;
 
 int gimb_dkm_create(const void* blob, size_t nbytes, int device, gimb_dkm** out);

@@ -133,11 +133,17 @@ def conv_refiner(x, y, flow, sd, key, radius, taps=None):
     def block(d, pre):
         d = _conv(d, sd, pre + ".0", padding=2, groups=d.shape[1])  # depthwise (dw=True), out_dim a multiple of in_dim
         d = F.relu(_bn(d, sd, pre + ".1"))
+        if taps is not None and f"refiner_dw{key}" not in taps:
+            taps[f"refiner_dw{key}"] = d
         return _conv(d, sd, pre + ".3")
 
     d = block(d, p + "block1")
+    if taps is not None and f"refiner_pw{key}" not in taps:
+        taps[f"refiner_pw{key}"] = d
     for i in range(8):
         d = block(d, f"{p}hidden_blocks.{i}")
+    if taps is not None and f"refiner_out{key}" not in taps:
+        taps[f"refiner_out{key}"] = d
     d = _conv(d, sd, p + "out_conv")
     return d[:, :-2], d[:, -2:]
 

@@ -10,7 +10,7 @@ sd = seeded_state_dict(0)
 taps = {}
 dkm_oracle.match(sd, im0, im1, h, w, up, taps=taps)
 m = DKMv3(None, h, w, upsample_preds=True); m.load_state_dict(sd); m = m.eval().cuda()
-names = ["dfn_flow16", "refiner_in16", "enc2", "enc4", "enc8", "enc16", "enc32", "gp32", "gp16"] + [f"{k}{s}" for s in (32, 16, 8, 4, 2, 1) for k in ("flow", "cert")] + \
+names = ["dfn_flow16", "refiner_in16", "refiner_dw16", "refiner_pw16", "refiner_out16", "enc2", "enc4", "enc8", "enc16", "enc32", "gp32", "gp16"] + [f"{k}{s}" for s in (32, 16, 8, 4, 2, 1) for k in ("flow", "cert")] + \
         [f"{k}{s}u" for s in (8, 4, 2, 1) for k in ("flow", "cert")]
 m.debug_taps = names
 m.upsample_res = up
