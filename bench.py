@@ -152,7 +152,8 @@ def run_reference(args):
               f"calls (requested {steps}/{warm}), median")
     line = {
         "impl": "reference", "metric": "image-pairs/sec @640x480 gim_loftr", "value": pps, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": steps_run, "warmup": warm_run, "requested_steps": steps, "requested_warmup": warm,
+        "ms_per_step": med * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": f"gim_loftr {W}x{H} batch-{args.batch} synthetic pairs", "matches_per_pair": M,
                    "device": "cpu"},
@@ -199,9 +200,15 @@ def run_ours(args):
         model(d)
         return d
 
+    # end-to-end: the images arrive as uint8 HWC host buffers (what cv2 / the ZEB loader hold, datasets/utils.py:108);
+    # /255, HWC -> CHW happen on the device (gimb_loftr_forward_host_u8).  The synthetic pairs live on the u8 grid, so
+    # this is the same input bit for bit.
+    u0_h = torch.round(c0_h * 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
+    u1_h = torch.round(c1_h * 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
+
     def step_host():
-        d = dict(color0=c0_h, color1=c1_h, image0=c0_h, image1=c1_h)
-        model(d)
+        d = dict(color0_u8=u0_h, color1_u8=u1_h)
+        model.forward_u8(d)
         return d
 
     def barrier():
@@ -314,7 +321,8 @@ def run_ours(args):
                    "l2": "inputs and activations exceed L2 (236 MB inputs per step)", "parallelism": f"pairs sharded dp{world}"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps},
+                "steps": e2e_steps, "entry": "gimb_loftr_forward_host_u8 (uint8 HWC pinned host images; /255 + HWC->CHW on device)",
+                "matches_last_step": int(last_h["b_ids"].numel())},
         "gpu_launches": launches,
         "roofline": roof,
         "stage_ms_per_step": stage_ms,
@@ -329,15 +337,139 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+DKM_TFLOP_PER_PAIR = 5.27  # 1.557 (672x896 pass) + 3.708 (1152x1536 pass), 2*MAC
+
+
+def run_dkm(args):
+    """BASELINE config 3: gim_dkm, 8 synthetic pairs per step at 672x896 (second pass at 1152x1536), seeded weights
+    (the trained checkpoint is absent from the reference tree).  match() is b = 1: a step is 8 consecutive calls."""
+    import torch.distributed as dist
+    from gim_b200 import DKMv3, synth
+    from gim_b200.dkm_params import seeded_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+    hh, ww = 672, 896
+    model = DKMv3(None, hh, ww, upsample_preds=True)
+    model.load_state_dict(seeded_state_dict(0))
+    model = model.eval().to(dev)
+    B = args.batch
+    a_h, b_h = synth.make_pairs(B, hh, ww, first=rank * B)
+    a_h, b_h = a_h.pin_memory(), b_h.pin_memory()
+    a_d, b_d = a_h.to(dev), b_h.to(dev)
+
+    def step_dev():
+        out = None
+        for i in range(B):
+            out = model.match(a_d[i:i + 1], b_d[i:i + 1])
+        return out
+
+    def step_host():
+        n = 0
+        for i in range(B):
+            warp, cert = model.match(a_h[i:i + 1].to(dev, non_blocking=True), b_h[i:i + 1].to(dev, non_blocking=True))
+            m, c = model.sample(warp, cert, 5000)     # the harness call (trainer/lightning.py:135-136)
+            n += int(m.cpu().shape[0]) + int(c.cpu().shape[0]) * 0
+        return n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = model.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), model.launch_count() - l0
+
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total, launches = timed(step_dev, steps, warm)
+    clocks = sampler.summary() if sampler else None
+    torch.manual_seed(0)
+    e2e_steps = min(steps, 3)
+    ms_e2e, _ = timed(step_host, e2e_steps, 1)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    value = world * B * steps / (ms_total / 1e3)
+    ach = DKM_TFLOP_PER_PAIR * B * steps / (ms_total / 1e3)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import dkm_oracle
+        torch.set_num_threads(min(os.cpu_count() or 1, 16))
+        sd = seeded_state_dict(0)
+        t0 = time.perf_counter()
+        dkm_oracle.match(sd, a_h[:1], b_h[:1], 224, 288, (384, 512))
+        dt = time.perf_counter() - t0
+        # the 672x896 / 1152x1536 pair costs 5.27 TFLOP; the sample is the same network at 224x288 / 384x512 (1/9 of the
+        # pixels), scaled by the pixel ratio - stated as such, not a full-size measurement
+        cpu = {"value": 1.0 / (dt * 9.0), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"oracle/dkm_oracle.py on pair 0 at 224x288 -> 384x512 ({dt:.1f} s), scaled x9 (pixel ratio) to the 672x896 workload"}
+    line = {
+        "metric": "image-pairs/sec @672x896 gim_dkm", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32-equivalent (fp16 2-term split operands, fp32 accumulate)", "data": "synthetic (seeded random weights)",
+        "config": {"workload": f"gim_dkm 672x896 batch-{B} synthetic pairs per GPU (second pass 1152x1536)", "pairs_per_gpu_per_step": B,
+                   "l2": "activations exceed L2 (the 1/1-scale refiner tensors alone are 2 x 1152 x 1536 x 24 x 4 B = 340 MB)",
+                   "parallelism": f"pairs sharded dp{world}"},
+        "clocks": clocks,
+        "e2e": {"value": world * B * e2e_steps / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(B * 2 * 3 * hh * ww * 4),
+                "d2h_bytes_per_step": int(B * 5000 * 5 * 4), "steps": e2e_steps,
+                "entry": "DKMv3.match + sample(5000): host fp32 images -> device, dense match, torch sampling, sparse matches -> host"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "whole match(): tcgen05 GEMM layers (ConvRefiner pointwise C x C = 83 % of the FLOPs) + helpers",
+                     "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
+                     "peak_source": pk["source"] + " bf16 sustained",
+                     "operand_format": "fp16 2-term split: 3 tcgen05.mma per logical MAC -> executed = 3x algorithmic"},
+        "cpu_baseline": cpu,
+    }
+    if world > 1:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step (BASELINE config: 32)")
+    ap.add_argument("--batch", type=int, default=None, help="pairs per GPU per step (BASELINE configs: 32 for gim_loftr, 8 for gim_dkm)")
+    ap.add_argument("--workload", default="loftr", choices=["loftr", "dkm"], help="loftr = the headline (config 2); dkm = config 3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 8 if args.workload == "dkm" else 32
+    if args.workload == "dkm" and args.impl == "ours":
+        return run_dkm(args)
     if args.impl == "reference":
         run_reference(args)
     else:

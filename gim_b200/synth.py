@@ -80,3 +80,25 @@ def make_pairs(n, h=480, w=640, first=0):
         c0.append(img)
         c1.append(warp_homography(img, random_homography(k)))
     return torch.stack(c0), torch.stack(c1)
+
+
+def pose_pair(k, h, w):
+    """A pose-consistent synthetic pair for the sweep / ZEB-format metrics: a fronto-parallel textured plane at depth 4 seen by
+    two cameras with the same intrinsics and a small relative motion.  Image 1 is image 0 warped by the plane-induced
+    homography H = K (R + t n^T / d) K^-1, so the ground-truth relative pose (T_0to1) and K are known exactly.
+    -> img0, img1 [3,h,w] float (u8 grid), K [3,3], T_0to1 [4,4] (float64 numpy)."""
+    rng = np.random.default_rng(5000 + k)
+    f = 0.9 * max(h, w)
+    K = np.array([[f, 0, w / 2.0], [0, f, h / 2.0], [0, 0, 1.0]])
+    ax, ay, az = rng.uniform(-0.04, 0.04, size=3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+    R = Rz @ Ry @ Rx
+    t = rng.uniform(-0.25, 0.25, size=3) * np.array([1.0, 1.0, 0.4])
+    n, d = np.array([0.0, 0.0, 1.0]), 4.0
+    Hm = K @ (R + np.outer(t, n) / d) @ np.linalg.inv(K)
+    img = base_image(k, h, w)
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = R, t
+    return img, warp_homography(img, Hm / Hm[2, 2]), K, T

@@ -20,6 +20,11 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 CASES = {  # name: (input h, w, h_resized, w_resized, upsample_res, synth pair index)
     "dkm_64x96_up128x192": (80, 112, 64, 96, (128, 192), 3),
     "dkm_96x128_up192x256": (120, 160, 96, 128, (192, 256), 5),
+    # big enough for the tensor-core Gram path of the GP (N = 14 * 18 = 252 tokens at 1/16) and several Cholesky blocks
+    "dkm_224x288_up320x416": (240, 320, 224, 288, (320, 416), 7),
+    # BASELINE config 3 geometry (672x896 -> 1152x1536 second pass): outputs stored on a stride-8 grid (the full tensors
+    # are 70 MB); GP with 588 / 2352 tokens, all refiner shapes at their real sizes
+    "dkm_672x896_up1152x1536_s8": (480, 640, 672, 896, (1152, 1536), 11),
 }
 
 
@@ -44,10 +49,15 @@ def case_images(name):
 
 def main():
     torch.manual_seed(0)
+    only = sys.argv[1:]
     for name, (ih, iw, h, w, up, _) in CASES.items():
+        if only and name not in only:
+            continue
         a, b = case_images(name)
         m = load_reference_dkm(h, w, up)
         warp, cert = m.match(a.float() / 255, b.float() / 255)
+        if name.endswith("_s8"):
+            warp, cert = warp[::8, ::8].contiguous(), cert[::8, ::8].contiguous()
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), im0_u8=a.numpy(), im1_u8=b.numpy(), h=h, w=w, up=np.array(up),
                             warp=warp.numpy(), certainty=cert.numpy())
         print(name, tuple(warp.shape), tuple(cert.shape), "certainty mean", float(cert.mean()), "nonzero", float((cert > 0).float().mean()))

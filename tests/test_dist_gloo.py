@@ -68,3 +68,34 @@ def test_pack_matches_keeps_large_pair_ids_exact():
             "mconf": torch.full((2,), 0.5)}
     rows = gdist.pack_matches([big], data)
     assert rows.dtype == torch.float64 and rows[:, 0].long().tolist() == [big, big]
+
+
+def test_sweep_units_and_assignment_are_deterministic_and_complete():
+    """the fixed mixed-resolution list is split into work units; every unit is owned by exactly one rank
+    and the greedy largest-first deal keeps the estimated load within 20 % of the mean for 2, 4 and 8 ranks."""
+    from gim_b200 import sweep
+    units = sweep.build_units()
+    ids = [p for u in units for p in u["ids"]]
+    assert ids == list(range(len(ids))) and len(ids) == 80
+    for world in (1, 2, 4, 8):
+        mine = sweep.assign(units, world)
+        flat = sorted(i for r in mine for i in r)
+        assert flat == list(range(len(units))) and mine == sweep.assign(units, world)
+        load = [sum(units[i]["cost"] for i in r) for r in mine]
+        assert max(load) <= 1.2 * sum(load) / world
+
+
+def test_pose_pair_is_consistent_with_its_homography():
+    """gim_b200.synth.pose_pair: image 1 is image 0 under the plane-induced homography of (K, R, t): points of the plane
+    have zero symmetric epipolar distance under the returned pose."""
+    import numpy as np
+    from gim_b200 import harness, synth
+    a, b, K, T = synth.pose_pair(4, 120, 160)
+    assert a.shape == b.shape == (3, 120, 160)
+    R, t = T[:3, :3], T[:3, 3]
+    Hm = K @ (R + np.outer(t, [0, 0, 1.0]) / 4.0) @ np.linalg.inv(K)
+    p0 = np.array([[20.0, 30.0], [100.0, 80.0], [140.0, 10.0], [60.0, 100.0], [80.0, 60.0], [10.0, 110.0]])
+    q = (Hm @ np.concatenate([p0, np.ones((6, 1))], 1).T).T
+    p1 = q[:, :2] / q[:, 2:]
+    m = harness.pair_metrics(p0, p1, K, K, T)
+    assert m["epi_errs"].max() < 1e-9

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from tests.test_dkm_oracle import DKM_CASES, TOL_CERT, TOL_WARP, load_dkm_case
+from tests.test_dkm_oracle import DKM_BIG_CASES, DKM_CASES, TOL_CERT, TOL_WARP, load_dkm_case
 
 pytestmark = pytest.mark.gpu
 
@@ -34,6 +34,42 @@ def test_dkm_match_vs_reference_golden(dkm_model, case):
     assert ew < TOL_WARP and ec < TOL_CERT
 
 
+@pytest.mark.parametrize("case", DKM_BIG_CASES)
+def test_dkm_config3_geometry_vs_reference_golden(dkm_model, case):
+    """BASELINE config 3 sizes (672x896, second pass 1152x1536; GP with 588 / 2352 tokens on the tensor-core Gram path and
+    74 Cholesky blocks): the golden holds the reference outputs on a stride-8 grid."""
+    import os
+    if not os.path.isfile(os.path.join(os.path.dirname(__file__), "golden", case + ".npz")):
+        pytest.skip("golden not generated")
+    w2, c2, warp, cert = _run(dkm_model, case)
+    w2, c2 = w2[::8, ::8], c2[::8, ::8]
+    assert w2.shape == warp.shape and c2.shape == cert.shape
+    ew, ec = (w2 - warp).abs().max().item(), (c2 - cert).abs().max().item()
+    print(case, "warp err", ew, "certainty err", ec)
+    assert ew < TOL_WARP and ec < TOL_CERT
+
+
+def test_dkm_sample_and_hloc_wrapper(dkm_model):
+    """sample() (torch, caller's RNG) and the hloc wrapper keep the reference's output contract (dkm.py:583-620,
+    hloc/matchers/dkm.py:92-154): shapes, value ranges, swapped-back keys, in-bounds keypoints."""
+    from gim_b200.dkm import HlocDKM
+    im0, im1, h, w, up, _, _ = load_dkm_case(DKM_CASES[1])
+    dkm_model.h_resized, dkm_model.w_resized, dkm_model.upsample_res = h, w, up
+    warp, cert = dkm_model.match(im0.cuda(), im1.cuda())
+    torch.manual_seed(0)
+    m, c = dkm_model.sample(warp, cert, 500)
+    assert m.shape[1] == 4 and m.shape[0] == c.shape[0] and 0 < m.shape[0] <= 500
+    assert m.abs().max().item() <= 1.0 and c.min().item() >= 0 and c.max().item() <= 1
+    wrap = HlocDKM()
+    wrap.net = dkm_model
+    wrap.h, wrap.w = h, w
+    pred = wrap({"image0": im0.cuda(), "image1": im1.cuda(), "name0": "a.jpg", "name1": "b.jpg"})
+    assert set(pred) == {"keypoints0", "keypoints1", "scores", "batch_indexes"}
+    k0, k1 = pred["keypoints0"], pred["keypoints1"]
+    assert k0.shape == k1.shape and k0.shape[0] == pred["scores"].shape[0] > 0
+    assert (k0[:, 0] <= im0.shape[3] - 1).all() and (k0[:, 1] <= im0.shape[2] - 1).all() and (k0 > 0).all()
+
+
 def test_dkm_stage_taps_vs_oracle(dkm_model):
     """Pyramid levels, GP outputs and the flow after every scale against the CPU oracle (same seeded weights)."""
     from gim_b200.dkm_params import seeded_state_dict
@@ -42,7 +78,8 @@ def test_dkm_stage_taps_vs_oracle(dkm_model):
     im0, im1, h, w, up, _, _ = load_dkm_case(case)
     taps = {}
     dkm_oracle.match(seeded_state_dict(0), im0, im1, h, w, up, taps=taps)
-    names = ["enc2", "enc4", "enc8", "enc16", "enc32", "gp32", "gp16"] + [f"flow{s}" for s in (32, 16, 8, 4, 2, 1)] + \
+    names = ["dfn_flow16", "refiner_in16", "refiner_dw16", "refiner_pw16", "refiner_out16",
+             "enc2", "enc4", "enc8", "enc16", "enc32", "gp32", "gp16"] + [f"flow{s}" for s in (32, 16, 8, 4, 2, 1)] + \
             [f"cert{s}" for s in (32, 16, 8, 4, 2, 1)] + [f"flow{s}u" for s in (8, 4, 2, 1)] + [f"cert{s}u" for s in (8, 4, 2, 1)]
     dkm_model.debug_taps = names
     try:
