@@ -55,6 +55,7 @@ EXPORTS = {
     "gimb_dkm_set_engine": (c_int, [c_void_p, c_int]),
     "gimb_dkm_launch_count": (c_uint64, [c_void_p]),
     "gimb_dkm_workspace_bytes": (c_int, [c_void_p] + [c_int] * 9 + [POINTER(c_size_t)]),
+    "gimb_kde_density": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "gimb_dkm_match": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

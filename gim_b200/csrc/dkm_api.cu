@@ -565,6 +565,14 @@ int gimb_dkm_workspace_bytes(gimb_dkm* h, int H1, int W1, int H2, int W2, int h_
   return dkm_run(h, a, nullptr, 0, true, bytes, nullptr);
 }
 
+int gimb_kde_density(const float* points, int n, float std, float* density, void* stream) {
+  GIMB_CHECK(points && density && n >= 0 && std > 0.f, "gimb_kde_density: bad argument");
+  GIMB_CHECK(((uintptr_t)points & 15) == 0, "gimb_kde_density: points must be 16-byte aligned");
+  Ctx ctx;
+  ctx.stream = (cudaStream_t)stream;
+  return dkm_kde(ctx, points, n, std, density);
+}
+
 int gimb_dkm_match(gimb_dkm* h, const float* im1, int H1, int W1, const float* im2, int H2, int W2, int h_resized, int w_resized,
                    int upsample_preds, int up_h, int up_w, void* workspace, size_t workspace_bytes, float* warp, float* certainty,
                    const gimb_dkm_taps* taps, void* stream) {

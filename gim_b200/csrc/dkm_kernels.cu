@@ -600,6 +600,27 @@ __global__ void finalize_kernel(const DkmFinalArgs a) {
   a.cert_out[(long long)y * (2 * a.ws) + half * a.ws + x] = c;
 }
 
+// Gaussian kernel density of n 4-D points (networks/dkm/utils/kde.py:17-26: exp(-cdist(x, x)^2 / (2 std^2)).sum(-1)) without
+// the n x n distance matrix: 256 points per CTA against tiles of 256 points staged in shared memory.
+__global__ void __launch_bounds__(256) kde_kernel(const float4* __restrict__ x, int n, float inv2s2, float* __restrict__ density) {
+  __shared__ float4 tile[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const float4 p = i < n ? x[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc = 0.f;
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    tile[threadIdx.x] = (j0 + threadIdx.x < n) ? x[j0 + threadIdx.x] : make_float4(1e18f, 1e18f, 1e18f, 1e18f);
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < 256; ++j) {
+      const float4 q = tile[j];
+      const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z, dw = p.w - q.w;
+      acc += __expf(-(dx * dx + dy * dy + dz * dz + dw * dw) * inv2s2);
+    }
+    __syncthreads();
+  }
+  if (i < n) density[i] = acc;
+}
+
 inline unsigned blocks(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -790,6 +811,11 @@ int dkm_apply_delta(Ctx& ctx, float* flow, float* certainty, bool cert_accumulat
 int dkm_split_head(Ctx& ctx, const float* head, int ld_head, int64_t rows, float* flow, float* certainty) {
   if (ctx.dry) return 0;
   split_head_kernel<<<blocks(rows, 256), 256, 0, ctx.stream>>>(head, ld_head, rows, flow, certainty);
+  GIMB_DKM_LAUNCH_END();
+}
+int dkm_kde(Ctx& ctx, const float* x, int n, float std, float* density) {
+  if (ctx.dry || n == 0) return 0;
+  kde_kernel<<<blocks(n, 256), 256, 0, ctx.stream>>>(reinterpret_cast<const float4*>(x), n, 1.f / (2.f * std * std), density);
   GIMB_DKM_LAUNCH_END();
 }
 int dkm_finalize(Ctx& ctx, const DkmFinalArgs& a) {

@@ -69,5 +69,7 @@ struct DkmFinalArgs {
   float* cert_out;         // [hs, 2 ws]
 };
 int dkm_finalize(Ctx& ctx, const DkmFinalArgs& a);
+// density[i] = sum_j exp(-|x_i - x_j|^2 / (2 std^2)) for n 4-D points (the balanced sampling of dkm.py:612-619)
+int dkm_kde(Ctx& ctx, const float* x /*[n,4], 16-byte aligned*/, int n, float std, float* density);
 
 }  // namespace gimb

@@ -258,11 +258,23 @@ class RegressionMatcher(DKMParams):
         good_certainty = certainty_raw[good] if "threshold" in self.sample_mode else certainty[good]
         if not balanced:
             return good_matches, good_certainty
-        density = (-torch.cdist(good_matches, good_matches) ** 2 / (2 * 0.1 ** 2)).exp().sum(dim=-1)
+        density = self._kde(good_matches, 0.1)
         p = 1 / (density + 1)
         p[density < 10] = 1e-7
         keep = torch.multinomial(p, num_samples=min(num, len(good_certainty)), replacement=False)
         return good_matches[keep], good_certainty[keep]
+
+    @staticmethod
+    def _kde(x, std):
+        """utils/kde.py:17-26.  CUDA: `gimb_kde_density` (no n x n distance matrix); CPU tensors: the reference formula."""
+        if x.device.type != "cuda":
+            return (-torch.cdist(x, x) ** 2 / (2 * std ** 2)).exp().sum(dim=-1)
+        x = x.to(torch.float32).contiguous()
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gimb_kde_density(x.data_ptr(), x.shape[0], float(std), out.data_ptr(),
+                                                    torch.cuda.current_stream(x.device).cuda_stream))
+        return out
 
     def to_pixel_coordinates(self, matches, H_A, W_A, H_B, W_B):  # dkm.py:652-656
         kA, kB = matches[..., :2], matches[..., 2:]

@@ -202,6 +202,9 @@ int gimb_dkm_workspace_bytes(gimb_dkm* h, int H1, int W1, int H2, int W2, int h_
                              int upsample_preds, int up_h, int up_w, size_t* bytes);
 /* match(): DEVICE fp32 NCHW images in [0, 1]; outputs warp [Hout, 2*Wout, 4] and certainty [Hout, 2*Wout] with
  * (Hout, Wout) = upsample_preds ? (up_h, up_w) : (h_resized, w_resized) - the tensors RegressionMatcher.match returns. */
+/* Replaces: networks/dkm/utils/kde.py:17-26 inside RegressionMatcher.sample (dkm.py:612): Gaussian kernel density of n
+ * 4-D matches, DEVICE pointers on the current device, without the n x n distance matrix. */
+int gimb_kde_density(const float* points, int n, float std, float* density, void* stream);
 int gimb_dkm_match(gimb_dkm* h, const float* im1, int H1, int W1, const float* im2, int H2, int W2,
                    int h_resized, int w_resized, int upsample_preds, int up_h, int up_w, void* workspace,
                    size_t workspace_bytes, float* warp, float* certainty, const gimb_dkm_taps* taps,

@@ -100,3 +100,15 @@ def test_dkm_stage_taps_vs_oracle(dkm_model):
         print(f"{k:8s} max|ref| {ref.abs().max().item():8.3f}  err {err:.3e}")
         worst = max(worst, err / scale)
         assert err / scale < 2e-4, k
+
+
+def test_kde_density_kernel_vs_reference_formula():
+    """the balanced-sampling density on the device vs utils/kde.py:23-25 (cdist form)."""
+    from gim_b200.dkm import RegressionMatcher
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(3001, 4, generator=g) * 2 - 1).cuda()
+    ref = (-torch.cdist(x.double(), x.double()) ** 2 / (2 * 0.1 ** 2)).exp().sum(dim=-1).float()
+    got = RegressionMatcher._kde(x, 0.1)
+    rel = ((got - ref).abs() / ref).max().item()
+    print("kde rel err", rel)
+    assert rel < 1e-4
