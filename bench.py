@@ -423,7 +423,8 @@ def run_dkm(args):
         torch.set_num_threads(min(os.cpu_count() or 1, 16))
         sd = seeded_state_dict(0)
         t0 = time.perf_counter()
-        dkm_oracle.match(sd, a_h[:1], b_h[:1], 224, 288, (384, 512))
+        with torch.no_grad():
+            dkm_oracle.match(sd, a_h[:1], b_h[:1], 224, 288, (384, 512))
         dt = time.perf_counter() - t0
         # the 672x896 / 1152x1536 pair costs 5.27 TFLOP; the sample is the same network at 224x288 / 384x512 (1/9 of the
         # pixels), scaled by the pixel ratio - stated as such, not a full-size measurement

@@ -33,6 +33,9 @@ struct RRBw { Conv c1, c2, c3; };
 struct Refiner {
   int cin = 0, hidden = 0, emb = 0, radius = 0, mult = 1, feat = 0;
   const float *emb_w = nullptr, *emb_b = nullptr;
+  const float* dw_wt[9];  // the same transposed and padded [25][pitch8(C)] (+ padded scale / bias) for the vectorised kernel
+  const float* dw_sp[9];
+  const float* dw_bp[9];
   const float* dw_w[9];   // depthwise weights [C, 25]
   const float* dw_s[9];   // folded BatchNorm (+ conv bias)
   const float* dw_b[9];
@@ -121,6 +124,9 @@ int build_dkm(gimb_dkm* m, Ctx& ctx) {
       GIMB_TRY(m->ws.find(bp + ".dw_w", &r.dw_w[k], &dsh));
       GIMB_TRY(m->ws.find(bp + ".dw_s", &r.dw_s[k]));
       GIMB_TRY(m->ws.find(bp + ".dw_b", &r.dw_b[k]));
+      GIMB_TRY(m->ws.find(bp + ".dw_wt", &r.dw_wt[k]));
+      GIMB_TRY(m->ws.find(bp + ".dw_sp", &r.dw_sp[k]));
+      GIMB_TRY(m->ws.find(bp + ".dw_bp", &r.dw_bp[k]));
       if (k == 0) { r.hidden = (int)dsh[0]; r.mult = r.hidden / r.cin; }
       GIMB_TRY(m->ws.load_conv(ctx, bp + ".pw", true, &r.pw[k]));
     }
@@ -270,7 +276,18 @@ int gp_regression(Fwd& F, gimb_dkm* m, int si, const ActT& fx, const ActT& fy, i
     GIMB_TRY(dkm_cos_gram(ctx, fx.f32, fy.f32, B, N, N, C, fy.pitch(), 0.2f, 0.f, Kxy));
   }
   GIMB_TRY(dkm_pos_basis(ctx, m->pos_w[si], m->pos_b[si], B, h, w, GP_DIM, f));
-  GIMB_TRY(dkm_chol_solve(ctx, Kyy, f, B, N, GP_DIM));
+  if (N > 2000) {
+    // REFERENCE QUIRK (dkm.py:352-356), reproduced because parity is defined against the unmodified reference: above 2000
+    // tokens the reference's per-sample inversion loop slices a batch-1 `sigma_noise` with [k:k+1]; for k >= 1 the slice is
+    // empty, so only K_yy[0] is inverted and that inverse is broadcast over the batch.  f does not depend on the batch
+    // entry, so one solve with K_yy[0] serves both.
+    GIMB_TRY(dkm_chol_solve(ctx, Kyy, f, 1, N, GP_DIM));
+    if (!ctx.dry)
+      for (int b = 1; b < B; ++b)
+        GIMB_CUDA(cudaMemcpyAsync(f + (size_t)b * N * GP_DIM, f, (size_t)N * GP_DIM * sizeof(float), cudaMemcpyDeviceToDevice, ctx.stream));
+  } else {
+    GIMB_TRY(dkm_chol_solve(ctx, Kyy, f, B, N, GP_DIM));
+  }
   GIMB_TRY(dkm_matmul_nn(ctx, Kxy, f, B, N, N, GP_DIM, mu, GP_DIM));
   A.release(mark);
   return 0;
@@ -288,7 +305,9 @@ int conv_refiner(Fwd& F, const Refiner& r, const float* x, const float* y, int l
   ActT ta = F.alloc(P, r.hidden, false, true);   // depthwise output: planes for the pointwise GEMM
   float* tb = A.alloc<float>(P * ldh);            // pointwise output (fp32, padded pitch)
   GIMB_CHECK(ctx.dry || !A.overflow, "dkm refiner: workspace exhausted");
-  // d = cat(x, x_hat, emb, local_corr)
+  // d = cat(x, x_hat, emb, local_corr); the pad channels up to the pitch are read (times zero weights) by the vectorised
+  // depthwise kernel, so they must not hold NaN bit patterns left in the workspace
+  GIMB_TRY(dkm_fill(ctx, d, P * ldd, 0.f));
   GIMB_TRY(dkm_copy_channels(ctx, x, (int64_t)P, r.feat, ld_xy, d, ldd, 0));
   GIMB_TRY(dkm_grid_sample(ctx, y, B, h, w, r.feat, ld_xy, flow, d, ldd, r.feat));
   GIMB_TRY(dkm_disp_emb(ctx, flow, B, h, w, r.emb_w, r.emb_b, r.emb, d, ldd, 2 * r.feat));
@@ -298,7 +317,9 @@ int conv_refiner(Fwd& F, const Refiner& r, const float* x, const float* y, int l
   int cur_c = r.cin, cur_ld = ldd;
   for (int k = 0; k < 9; ++k) {
     const int mult = k == 0 ? r.mult : 1;
-    if (F.tc()) {
+    if (F.tc() && mult == 1) {
+      GIMB_TRY(dkm_depthwise5x5_v4(ctx, cur, B, h, w, cur_c, cur_ld, r.dw_wt[k], r.dw_sp[k], r.dw_bp[k], ldh, nullptr, 0, ta.planes()));
+    } else if (F.tc()) {
       GIMB_TRY(dkm_depthwise5x5(ctx, cur, B, h, w, cur_c, cur_ld, mult, r.dw_w[k], r.dw_s[k], r.dw_b[k], nullptr, 0, ta.planes()));
     } else {
       GIMB_TRY(dkm_depthwise5x5(ctx, cur, B, h, w, cur_c, cur_ld, mult, r.dw_w[k], r.dw_s[k], r.dw_b[k], ta.f32, r.hidden, nullptr));

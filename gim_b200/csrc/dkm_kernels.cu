@@ -555,6 +555,89 @@ __global__ void depthwise5x5_kernel(const float* __restrict__ in, int B, int h, 
   }
 }
 
+// Depthwise 5x5 + folded BatchNorm + ReLU, channel multiplier 1, vectorised: a thread owns 4 channels (one float4 of the
+// NHWC row) and a 4 (x) by 2 (y) patch of output pixels, walks the 6 input rows of the patch once (8 float4 loads per row)
+// and reuses every loaded pixel for up to 10 outputs - 6 loads per output pixel instead of 25.  Weights / scale / bias come
+// transposed and padded ([25][Cp], Cp = plane pitch) so that consecutive threads read consecutive float4s.
+__global__ void __launch_bounds__(128) depthwise5x5_v4_kernel(const float* __restrict__ in, int B, int h, int w, int C, int ld_in,
+                                                              const float* __restrict__ wt /*[25][Cp]*/, const float* __restrict__ scale,
+                                                              const float* __restrict__ bias, int Cp, float* __restrict__ out, int ld_out,
+                                                              __half* __restrict__ hi, __half* __restrict__ lo, int ldp) {
+  const int cq = blockIdx.y * 128 + threadIdx.x;  // channel quad
+  if (cq * 4 >= Cp) return;
+  const int tiles_x = (w + 3) >> 2, tiles_y = (h + 1) >> 1;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int x0 = tx * 4, y0 = ty * 2;
+  const int c = cq * 4;
+  float4 acc[2][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* base = in + (long long)b * h * w * ld_in + c;
+#pragma unroll
+  for (int ry = 0; ry < 6; ++ry) {  // input rows y0 - 2 .. y0 + 3
+    const int yy = y0 + ry - 2;
+    if (yy < 0 || yy >= h) continue;
+    float4 row[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int xx = x0 + i - 2;
+      row[i] = (xx >= 0 && xx < w && c < C) ? __ldg(reinterpret_cast<const float4*>(base + ((long long)yy * w + xx) * ld_in))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int dy = ry - r;  // kernel row used by output row r
+      if (dy < 0 || dy > 4) continue;
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wt + (long long)(dy * 5 + dx) * Cp + c));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = row[i + dx];
+          acc[r][i].x = fmaf(wv.x, v.x, acc[r][i].x);
+          acc[r][i].y = fmaf(wv.y, v.y, acc[r][i].y);
+          acc[r][i].z = fmaf(wv.z, v.z, acc[r][i].z);
+          acc[r][i].w = fmaf(wv.w, v.w, acc[r][i].w);
+        }
+      }
+    }
+  }
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c)), bi = __ldg(reinterpret_cast<const float4*>(bias + c));
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int y = y0 + r;
+    if (y >= h) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = x0 + i;
+      if (x >= w) continue;
+      float4 v;  // channels >= C have zero weights / scale / bias: exactly 0 (the GEMM's K padding)
+      v.x = fmaxf(fmaf(acc[r][i].x, sc.x, bi.x), 0.f);
+      v.y = fmaxf(fmaf(acc[r][i].y, sc.y, bi.y), 0.f);
+      v.z = fmaxf(fmaf(acc[r][i].z, sc.z, bi.z), 0.f);
+      v.w = fmaxf(fmaf(acc[r][i].w, sc.w, bi.w), 0.f);
+      const long long pix = ((long long)b * h + y) * w + x;
+      if (out && c < C) *reinterpret_cast<float4*>(out + pix * ld_out + c) = v;
+      if (hi) {
+        const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn((v.x - f01.x) * kSplitScale, (v.y - f01.y) * kSplitScale);
+        const __half2 l23 = __floats2half2_rn((v.z - f23.x) * kSplitScale, (v.w - f23.y) * kSplitScale);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const unsigned*>(&h01); hv.y = *reinterpret_cast<const unsigned*>(&h23);
+        lv.x = *reinterpret_cast<const unsigned*>(&l01); lv.y = *reinterpret_cast<const unsigned*>(&l23);
+        *reinterpret_cast<uint2*>(hi + pix * ldp + c) = hv;
+        *reinterpret_cast<uint2*>(lo + pix * ldp + c) = lv;
+      }
+    }
+  }
+}
+
 __global__ void apply_delta_kernel(float* __restrict__ flow, float* __restrict__ cert, int accumulate, const float* __restrict__ head,
                                    int ld_head, long long npix, float fx, float fy) {
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -798,6 +881,17 @@ int dkm_depthwise5x5(Ctx& ctx, const float* in, int B, int h, int w, int Cin, in
   depthwise5x5_kernel<<<blocks((long long)B * h * w * cpad, 256), 256, 0, ctx.stream>>>(in, B, h, w, Cin, ld_in, mult, wt, scale, bias, out,
                                                                                         ld_out, planes ? planes->hi : nullptr,
                                                                                         planes ? planes->lo : nullptr, planes ? planes->ld : 0);
+  GIMB_DKM_LAUNCH_END();
+}
+int dkm_depthwise5x5_v4(Ctx& ctx, const float* in, int B, int h, int w, int C, int ld_in, const float* wt_t, const float* scale_p,
+                        const float* bias_p, int Cp, float* out, int ld_out, const SplitPlanes* planes) {
+  GIMB_CHECK(Cp % 4 == 0 && ld_in % 4 == 0 && ld_in >= Cp - 3 && (!planes || planes->ld == Cp) && (!out || ld_out % 4 == 0),
+             "dkm_depthwise5x5_v4: pitches must be multiples of 4 and cover the padded channel count");
+  if (ctx.dry) return 0;
+  const int cq = Cp / 4;
+  dim3 grid(B * ((h + 1) / 2) * ((w + 3) / 4), cdiv(cq, 128));  // pixel tiles in x (up to 2^31 - 1 blocks)
+  depthwise5x5_v4_kernel<<<grid, 128, 0, ctx.stream>>>(in, B, h, w, C, ld_in, wt_t, scale_p, bias_p, Cp, out, ld_out,
+                                                       planes ? planes->hi : nullptr, planes ? planes->lo : nullptr, planes ? planes->ld : 0);
   GIMB_DKM_LAUNCH_END();
 }
 int dkm_apply_delta(Ctx& ctx, float* flow, float* certainty, bool cert_accumulate, const float* head, int ld_head, int B, int hs, int ws,

@@ -51,6 +51,10 @@ int dkm_local_corr(Ctx& ctx, const float* x, const float* y, int B, int h, int w
 // depthwise 5x5 (channel multiplier `mult`) + folded BatchNorm + ReLU; fp32 and / or split planes out
 int dkm_depthwise5x5(Ctx& ctx, const float* in, int B, int h, int w, int Cin, int ld_in, int mult, const float* wt /*[Cout,25]*/,
                      const float* scale, const float* bias, float* out, int ld_out, const SplitPlanes* planes);
+// the same for channel multiplier 1 with transposed, padded parameters (wt_t [25][Cp], scale_p / bias_p [Cp], Cp = plane pitch):
+// 4 channels x (4 x 2) pixels per thread, float4 loads
+int dkm_depthwise5x5_v4(Ctx& ctx, const float* in, int B, int h, int w, int C, int ld_in, const float* wt_t, const float* scale_p,
+                        const float* bias_p, int Cp, float* out, int ld_out, const SplitPlanes* planes);
 // flow += ins * disp / (4w, 4h); certainty (+)= delta   (dkm.py:501-510); head = [B, hw, ld_head] with (certainty, dx, dy)
 int dkm_apply_delta(Ctx& ctx, float* flow, float* certainty, bool cert_accumulate, const float* head, int ld_head, int B, int hs, int ws,
                     float ins, int W, int H);

@@ -81,6 +81,11 @@ def packed_dkm_tensors(sd):
             out[f"ref.{s}.b{k}.dw_w"] = w.reshape(w.shape[0], 25).contiguous()
             out[f"ref.{s}.b{k}.dw_s"] = bs.contiguous()
             out[f"ref.{s}.b{k}.dw_b"] = (bs * f(blk + ".0.bias") + bb).contiguous()
+            cp = (w.shape[0] + 31) // 32 * 32  # transposed + zero-padded copies for the vectorised depthwise kernel
+            wt = torch.zeros(25, cp); wt[:, : w.shape[0]] = w.reshape(w.shape[0], 25).t()
+            sp = torch.zeros(cp); sp[: w.shape[0]] = out[f"ref.{s}.b{k}.dw_s"]
+            bp = torch.zeros(cp); bp[: w.shape[0]] = out[f"ref.{s}.b{k}.dw_b"]
+            out[f"ref.{s}.b{k}.dw_wt"], out[f"ref.{s}.b{k}.dw_sp"], out[f"ref.{s}.b{k}.dw_bp"] = wt, sp, bp
             conv_bias(f"ref.{s}.b{k}.pw", blk + ".3")
         conv_bias(f"ref.{s}.out", r + ".out_conv", pad_to=8)
     return out

@@ -72,7 +72,18 @@ def gp(x, y, sd, pre, sigma_noise=0.1):
     xr, yr, fr = (t.flatten(2).transpose(1, 2) for t in (x, y, f))
     K_yy = cos_kernel(yr, yr)
     K_xy = cos_kernel(xr, yr)
-    K_yy_inv = torch.linalg.inv(K_yy + sigma_noise * torch.eye(h2 * w2)[None])
+    A = K_yy + sigma_noise * torch.eye(h2 * w2)[None]
+    if h2 * w2 > 2000:
+        # REFERENCE QUIRK, kept because parity is defined against the unmodified reference (dkm.py:352-356): above 2000
+        # tokens it inverts "one matrix at a time" with `sigma_noise[k:k+1]`, but sigma_noise has batch size 1, so for
+        # k >= 1 the slice is empty, the sum broadcasts to an empty batch and only the FIRST matrix is inverted; the matmul
+        # below then broadcasts that one inverse over the whole batch (the support->query half uses the query->support
+        # half's K_yy^-1).  672x896 inputs have 2352 tokens at 1/16 and take this branch.
+        K_yy_inv = torch.linalg.inv(A[0:1])
+    else:
+        # one matrix at a time: the batched routine runs the same LAPACK factorisation per matrix, and its MKL build fails
+        # on some hosts ("SLASWP parameter 6")
+        K_yy_inv = torch.cat([torch.linalg.inv(A[k:k + 1]) for k in range(b)])
     mu = K_xy.matmul(K_yy_inv.matmul(fr))
     return mu.transpose(1, 2).reshape(b, -1, h1, w1)
 

@@ -24,11 +24,21 @@ def _run(m, case):
     return w2.cpu(), c2.cpu(), warp, cert
 
 
+def _cert_err(c2, cert, warp):
+    """Certainty error away from the reference's hard threshold: match() zeroes the certainty where |flow| > 1
+    (dkm.py:721-723), a step function of the flow - a pixel whose (clamped) warp coordinate sits within 1e-4 of +-1 may
+    land on either side for a 1e-5 flow difference.  Those pixels are compared on the warp only."""
+    edge = (warp.abs() >= 1 - 1e-4).any(dim=-1)
+    d = (c2 - cert).abs()
+    print("certainty: pixels at the |flow| = 1 step:", int(edge.sum()), "of", edge.numel(), "; max err there", d[edge].max().item() if edge.any() else 0.0)
+    return d[~edge].max().item()
+
+
 @pytest.mark.parametrize("case", DKM_CASES)
 def test_dkm_match_vs_reference_golden(dkm_model, case):
     w2, c2, warp, cert = _run(dkm_model, case)
     assert w2.shape == warp.shape and c2.shape == cert.shape
-    ew, ec = (w2 - warp).abs().max().item(), (c2 - cert).abs().max().item()
+    ew, ec = (w2 - warp).abs().max().item(), _cert_err(c2, cert, warp)
     print(case, "warp err", ew, "certainty err", ec, "launches", dkm_model.launch_count())
     assert dkm_model.launch_count() > 0
     assert ew < TOL_WARP and ec < TOL_CERT
@@ -44,7 +54,7 @@ def test_dkm_config3_geometry_vs_reference_golden(dkm_model, case):
     w2, c2, warp, cert = _run(dkm_model, case)
     w2, c2 = w2[::8, ::8], c2[::8, ::8]
     assert w2.shape == warp.shape and c2.shape == cert.shape
-    ew, ec = (w2 - warp).abs().max().item(), (c2 - cert).abs().max().item()
+    ew, ec = (w2 - warp).abs().max().item(), _cert_err(c2, cert, warp)
     print(case, "warp err", ew, "certainty err", ec)
     assert ew < TOL_WARP and ec < TOL_CERT
 

@@ -201,3 +201,30 @@ def test_u8_entry_matches_float_entry_and_masks(model):
         assert torch.equal(d2[k], ref[k].cpu()), k
     assert (d2["mkpts1_f"] - ref["mkpts1_f"].cpu()).abs().max().item() < 1e-4
     assert d2["b_ids"].numel() > 100
+
+
+def test_corr_range_flag_falls_back_to_exact_sweeps():
+    """csrc/corr_sweep.cu: a softmax sum outside the safe range of the fixed exponent reference raises the device flag and
+    the forward repeats the coarse matching with the exact (online-max) sweeps.  Forced here by biasing the reference by
+    +200 (every exponential flushes to zero); the results must still equal the golden and the fallback must be counted.
+    A subprocess, because the bias is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys; sys.path.insert(0, '.')\n"
+        "from gim_b200 import LoFTR, get_default_config, load_default_weights\n"
+        "from tests.goldens import load_case, assert_matches_equal\n"
+        "m = LoFTR(get_default_config()); m.load_state_dict(load_default_weights()); m = m.eval().cuda()\n"
+        "data, gold = load_case('small_b2_240x320')\n"
+        "d = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}\n"
+        "m(d); torch.cuda.synchronize()\n"
+        "assert_matches_equal(d, gold)\n"
+        "print('FALLBACKS', m.corr_fallbacks())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for bias, expect in (("200", True), ("0", False)):
+        env = dict(os.environ, GIMB_CORR_GBIAS=bias)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        n = int(r.stdout.strip().split("FALLBACKS")[-1])
+        assert (n > 0) == expect, (bias, n)
