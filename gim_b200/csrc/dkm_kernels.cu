@@ -563,10 +563,14 @@ __global__ void __launch_bounds__(128) depthwise5x5_v4_kernel(const float* __res
                                                               const float* __restrict__ wt /*[25][Cp]*/, const float* __restrict__ scale,
                                                               const float* __restrict__ bias, int Cp, float* __restrict__ out, int ld_out,
                                                               __half* __restrict__ hi, __half* __restrict__ lo, int ldp) {
-  const int cq = blockIdx.y * 128 + threadIdx.x;  // channel quad
-  if (cq * 4 >= Cp) return;
+  // work items = (pixel tile, channel quad) pairs, channel quads fastest: every thread is busy whatever C is (C = 24 has
+  // only 8 quads) and consecutive threads read consecutive float4s
+  const int cq_total = Cp >> 2;
+  const long long item = blockIdx.x * 128ll + threadIdx.x;
   const int tiles_x = (w + 3) >> 2, tiles_y = (h + 1) >> 1;
-  int t = blockIdx.x;
+  if (item >= (long long)B * tiles_y * tiles_x * cq_total) return;
+  const int cq = (int)(item % cq_total);
+  int t = (int)(item / cq_total);
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
@@ -888,9 +892,8 @@ int dkm_depthwise5x5_v4(Ctx& ctx, const float* in, int B, int h, int w, int C, i
   GIMB_CHECK(Cp % 4 == 0 && ld_in % 4 == 0 && ld_in >= Cp - 3 && (!planes || planes->ld == Cp) && (!out || ld_out % 4 == 0),
              "dkm_depthwise5x5_v4: pitches must be multiples of 4 and cover the padded channel count");
   if (ctx.dry) return 0;
-  const int cq = Cp / 4;
-  dim3 grid(B * ((h + 1) / 2) * ((w + 3) / 4), cdiv(cq, 128));  // pixel tiles in x (up to 2^31 - 1 blocks)
-  depthwise5x5_v4_kernel<<<grid, 128, 0, ctx.stream>>>(in, B, h, w, C, ld_in, wt_t, scale_p, bias_p, Cp, out, ld_out,
+  const long long items = (long long)B * ((h + 1) / 2) * ((w + 3) / 4) * (Cp / 4);
+  depthwise5x5_v4_kernel<<<blocks(items, 128), 128, 0, ctx.stream>>>(in, B, h, w, C, ld_in, wt_t, scale_p, bias_p, Cp, out, ld_out,
                                                        planes ? planes->hi : nullptr, planes ? planes->lo : nullptr, planes ? planes->ld : 0);
   GIMB_DKM_LAUNCH_END();
 }
