@@ -307,7 +307,7 @@ int conv_refiner(Fwd& F, const Refiner& r, const float* x, const float* y, int l
   GIMB_CHECK(ctx.dry || !A.overflow, "dkm refiner: workspace exhausted");
   // d = cat(x, x_hat, emb, local_corr); the pad channels up to the pitch are read (times zero weights) by the vectorised
   // depthwise kernel, so they must not hold NaN bit patterns left in the workspace
-  GIMB_TRY(dkm_fill(ctx, d, P * ldd, 0.f));
+  GIMB_TRY(dkm_zero_pad_channels(ctx, d, (int64_t)P, r.cin, ldd));
   GIMB_TRY(dkm_copy_channels(ctx, x, (int64_t)P, r.feat, ld_xy, d, ldd, 0));
   GIMB_TRY(dkm_grid_sample(ctx, y, B, h, w, r.feat, ld_xy, flow, d, ldd, r.feat));
   GIMB_TRY(dkm_disp_emb(ctx, flow, B, h, w, r.emb_w, r.emb_b, r.emb, d, ldd, 2 * r.feat));
@@ -317,8 +317,8 @@ int conv_refiner(Fwd& F, const Refiner& r, const float* x, const float* y, int l
   int cur_c = r.cin, cur_ld = ldd;
   for (int k = 0; k < 9; ++k) {
     const int mult = k == 0 ? r.mult : 1;
-    if (F.tc() && mult == 1) {
-      GIMB_TRY(dkm_depthwise5x5_v4(ctx, cur, B, h, w, cur_c, cur_ld, r.dw_wt[k], r.dw_sp[k], r.dw_bp[k], ldh, nullptr, 0, ta.planes()));
+    if (F.tc() && (mult == 1 || mult == 2)) {
+      GIMB_TRY(dkm_depthwise5x5_v4(ctx, cur, B, h, w, r.hidden, cur_ld, r.dw_wt[k], r.dw_sp[k], r.dw_bp[k], ldh, nullptr, 0, ta.planes(), mult));
     } else if (F.tc()) {
       GIMB_TRY(dkm_depthwise5x5(ctx, cur, B, h, w, cur_c, cur_ld, mult, r.dw_w[k], r.dw_s[k], r.dw_b[k], nullptr, 0, ta.planes()));
     } else {

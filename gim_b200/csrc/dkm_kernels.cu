@@ -108,6 +108,13 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int B, int C, 
   out[idx] = c < C ? in[(b * C + c) * hw + p] : 0.f;
 }
 
+__global__ void zero_pad_channels_kernel(float* __restrict__ x, long long rows, int C, int ld) {
+  const int padw = ld - C;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= rows * padw) return;
+  const long long r = idx / padw;
+  x[r * ld + C + (int)(idx - r * padw)] = 0.f;
+}
 __global__ void fill_kernel(float* dst, size_t n, float v) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = v;
@@ -188,27 +195,27 @@ __global__ void pos_basis_kernel(const float* __restrict__ w, const float* __res
 
 // ---- blocked Cholesky (lower), block size 32
 constexpr int NB = 32;
+// diagonal block: one warp, lane = row held in registers, column values exchanged by shuffles (the shared-memory version
+// spent 29 us per block in a serial chain of dependent smem reads; this one ~2 us)
 __global__ void __launch_bounds__(32) chol_diag_kernel(float* __restrict__ A, int N, int k0, int kb) {
-  __shared__ float a[NB][NB + 1];
   float* Ab = A + (long long)blockIdx.x * N * N;
   const int lane = threadIdx.x;
-  for (int r = 0; r < kb; ++r) a[r][lane] = (lane < kb) ? Ab[(long long)(k0 + r) * N + k0 + lane] : 0.f;
-  __syncwarp();
-  for (int j = 0; j < kb; ++j) {
-    const float d = sqrtf(a[j][j]);
-    __syncwarp();
-    if (lane == j) a[j][j] = d;
-    if (lane > j && lane < kb) a[lane][j] = a[lane][j] / d;
-    __syncwarp();
-    // trailing update of the lower triangle: a[i][k] -= l[i][j] * l[k][j] for j < k <= i ; lane = i
-    if (lane > j && lane < kb) {
-      const float lij = a[lane][j];
-      for (int k = j + 1; k <= lane; ++k) a[lane][k] -= lij * a[k][j];
-    }
-    __syncwarp();
+  float a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c)  // rows / columns beyond kb: identity (keeps the arithmetic finite, never written back)
+    a[c] = (lane < kb && c < kb) ? Ab[(long long)(k0 + lane) * N + k0 + c] : (lane == c ? 1.f : 0.f);
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const float d = sqrtf(__shfl_sync(0xffffffffu, a[j], j));
+    float lij = a[j] / d;          // lanes i > j: l[i][j]; lanes < j hold the (unused) upper triangle
+    if (lane == j) lij = d;
+    a[j] = lij;
+#pragma unroll
+    for (int k = j + 1; k < NB; ++k) a[k] -= lij * __shfl_sync(0xffffffffu, lij, k);  // a[i][k] -= l[i][j] l[k][j]
   }
-  for (int r = 0; r < kb; ++r)
-    if (lane < kb) Ab[(long long)(k0 + r) * N + k0 + lane] = (lane <= r) ? a[r][lane] : 0.f;
+#pragma unroll
+  for (int c = 0; c < NB; ++c)
+    if (lane < kb && c < kb) Ab[(long long)(k0 + lane) * N + k0 + c] = c <= lane ? a[c] : 0.f;
 }
 // rows below the diagonal block: L21 = A21 * L11^-T   (thread per row, forward substitution over the 32 columns)
 __global__ void __launch_bounds__(128) chol_panel_kernel(float* __restrict__ A, int N, int k0, int kb) {
@@ -559,6 +566,7 @@ __global__ void depthwise5x5_kernel(const float* __restrict__ in, int B, int h, 
 // NHWC row) and a 4 (x) by 2 (y) patch of output pixels, walks the 6 input rows of the patch once (8 float4 loads per row)
 // and reuses every loaded pixel for up to 10 outputs - 6 loads per output pixel instead of 25.  Weights / scale / bias come
 // transposed and padded ([25][Cp], Cp = plane pitch) so that consecutive threads read consecutive float4s.
+template <bool kMult2>  // kMult2: channel multiplier 2 (output channel co reads input channel co / 2; block1 of the 1/1 refiner)
 __global__ void __launch_bounds__(128) depthwise5x5_v4_kernel(const float* __restrict__ in, int B, int h, int w, int C, int ld_in,
                                                               const float* __restrict__ wt /*[25][Cp]*/, const float* __restrict__ scale,
                                                               const float* __restrict__ bias, int Cp, float* __restrict__ out, int ld_out,
@@ -581,7 +589,7 @@ __global__ void __launch_bounds__(128) depthwise5x5_v4_kernel(const float* __res
   for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* base = in + (long long)b * h * w * ld_in + c;
+  const float* base = in + (long long)b * h * w * ld_in + (kMult2 ? c / 2 : c);
 #pragma unroll
   for (int ry = 0; ry < 6; ++ry) {  // input rows y0 - 2 .. y0 + 3
     const int yy = y0 + ry - 2;
@@ -590,8 +598,15 @@ __global__ void __launch_bounds__(128) depthwise5x5_v4_kernel(const float* __res
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int xx = x0 + i - 2;
-      row[i] = (xx >= 0 && xx < w && c < C) ? __ldg(reinterpret_cast<const float4*>(base + ((long long)yy * w + xx) * ld_in))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (xx >= 0 && xx < w && c < C) {
+        if (kMult2) {
+          const float2 v2 = __ldg(reinterpret_cast<const float2*>(base + ((long long)yy * w + xx) * ld_in));
+          row[i] = make_float4(v2.x, v2.x, v2.y, v2.y);
+        } else {
+          row[i] = __ldg(reinterpret_cast<const float4*>(base + ((long long)yy * w + xx) * ld_in));
+        }
+      }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -755,6 +770,11 @@ int dkm_fill(Ctx& ctx, float* dst, size_t n, float v) {
   fill_kernel<<<blocks((long long)n, 256), 256, 0, ctx.stream>>>(dst, n, v);
   GIMB_DKM_LAUNCH_END();
 }
+int dkm_zero_pad_channels(Ctx& ctx, float* x, int64_t rows, int C, int ld) {
+  if (ctx.dry || rows == 0 || ld == C) return 0;
+  zero_pad_channels_kernel<<<blocks(rows * (ld - C), 256), 256, 0, ctx.stream>>>(x, rows, C, ld);
+  GIMB_DKM_LAUNCH_END();
+}
 int dkm_grid_flow(Ctx& ctx, float* flow, int B, int h, int w) {
   if (ctx.dry) return 0;
   grid_flow_kernel<<<blocks((long long)B * h * w, 256), 256, 0, ctx.stream>>>(flow, B, h, w);
@@ -888,13 +908,20 @@ int dkm_depthwise5x5(Ctx& ctx, const float* in, int B, int h, int w, int Cin, in
   GIMB_DKM_LAUNCH_END();
 }
 int dkm_depthwise5x5_v4(Ctx& ctx, const float* in, int B, int h, int w, int C, int ld_in, const float* wt_t, const float* scale_p,
-                        const float* bias_p, int Cp, float* out, int ld_out, const SplitPlanes* planes) {
-  GIMB_CHECK(Cp % 4 == 0 && ld_in % 4 == 0 && ld_in >= Cp - 3 && (!planes || planes->ld == Cp) && (!out || ld_out % 4 == 0),
+                        const float* bias_p, int Cp, float* out, int ld_out, const SplitPlanes* planes, int mult) {
+  GIMB_CHECK(Cp % 4 == 0 && ld_in % 4 == 0 && (mult == 2 || ld_in >= Cp - 3) && (mult == 1 || mult == 2) &&
+                 (!planes || planes->ld == Cp) && (!out || ld_out % 4 == 0),
              "dkm_depthwise5x5_v4: pitches must be multiples of 4 and cover the padded channel count");
   if (ctx.dry) return 0;
   const long long items = (long long)B * ((h + 1) / 2) * ((w + 3) / 4) * (Cp / 4);
-  depthwise5x5_v4_kernel<<<blocks(items, 128), 128, 0, ctx.stream>>>(in, B, h, w, C, ld_in, wt_t, scale_p, bias_p, Cp, out, ld_out,
-                                                       planes ? planes->hi : nullptr, planes ? planes->lo : nullptr, planes ? planes->ld : 0);
+  if (mult == 2)
+    depthwise5x5_v4_kernel<true><<<blocks(items, 128), 128, 0, ctx.stream>>>(in, B, h, w, C, ld_in, wt_t, scale_p, bias_p, Cp, out, ld_out,
+                                                                             planes ? planes->hi : nullptr, planes ? planes->lo : nullptr,
+                                                                             planes ? planes->ld : 0);
+  else
+    depthwise5x5_v4_kernel<false><<<blocks(items, 128), 128, 0, ctx.stream>>>(in, B, h, w, C, ld_in, wt_t, scale_p, bias_p, Cp, out, ld_out,
+                                                                              planes ? planes->hi : nullptr, planes ? planes->lo : nullptr,
+                                                                              planes ? planes->ld : 0);
   GIMB_DKM_LAUNCH_END();
 }
 int dkm_apply_delta(Ctx& ctx, float* flow, float* certainty, bool cert_accumulate, const float* head, int ld_head, int B, int hs, int ws,

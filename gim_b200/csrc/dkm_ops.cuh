@@ -16,6 +16,7 @@ int dkm_maxpool3x3s2(Ctx& ctx, const float* in, int B, int H, int W, int C, floa
 // dst[r, c_off + c] = src[r, c]  (torch.cat along channels); optional split planes of the destination slice
 int dkm_copy_channels(Ctx& ctx, const float* src, int64_t rows, int C, int ld_src, float* dst, int ld_dst, int c_off);
 int dkm_fill(Ctx& ctx, float* dst, size_t n, float v);
+int dkm_zero_pad_channels(Ctx& ctx, float* x, int64_t rows, int C, int ld);  // x[r, C .. ld) = 0
 // x = hi + lo * 2^-8 (split planes back to fp32) ; NCHW -> NHWC with channel pitch ld (pad channels zeroed)
 int planes_to_f32(Ctx& ctx, const SplitPlanes& sp, int64_t rows, int C, float* out, int ld_out);
 int nchw_to_nhwc(Ctx& ctx, const float* in, int B, int C, int H, int W, float* out, int ld);
@@ -51,10 +52,10 @@ int dkm_local_corr(Ctx& ctx, const float* x, const float* y, int B, int h, int w
 // depthwise 5x5 (channel multiplier `mult`) + folded BatchNorm + ReLU; fp32 and / or split planes out
 int dkm_depthwise5x5(Ctx& ctx, const float* in, int B, int h, int w, int Cin, int ld_in, int mult, const float* wt /*[Cout,25]*/,
                      const float* scale, const float* bias, float* out, int ld_out, const SplitPlanes* planes);
-// the same for channel multiplier 1 with transposed, padded parameters (wt_t [25][Cp], scale_p / bias_p [Cp], Cp = plane pitch):
+// the same for channel multiplier 1 or 2 (C = OUTPUT channels) with transposed, padded parameters (wt_t [25][Cp], scale_p / bias_p [Cp], Cp = plane pitch):
 // 4 channels x (4 x 2) pixels per thread, float4 loads
 int dkm_depthwise5x5_v4(Ctx& ctx, const float* in, int B, int h, int w, int C, int ld_in, const float* wt_t, const float* scale_p,
-                        const float* bias_p, int Cp, float* out, int ld_out, const SplitPlanes* planes);
+                        const float* bias_p, int Cp, float* out, int ld_out, const SplitPlanes* planes, int mult = 1);
 // flow += ins * disp / (4w, 4h); certainty (+)= delta   (dkm.py:501-510); head = [B, hw, ld_head] with (certainty, dx, dy)
 int dkm_apply_delta(Ctx& ctx, float* flow, float* certainty, bool cert_accumulate, const float* head, int ld_head, int B, int hs, int ws,
                     float ins, int W, int H);

@@ -107,3 +107,52 @@ def test_position_encoding_table_matches_oracle():
     t = position_encoding_table(256, 6, 9)
     ref = position_encoding(256, 6, 9).permute(1, 2, 0).reshape(54, 256)
     assert torch.equal(t, ref)
+
+
+# ----------------------------------------------------------------------------- gim_dkm boundary
+def test_dkm_module_mirrors_reference_contract():
+    """DKMv3(...) keeps the reference builder's signature, the caller-overwritten attributes (trainer/lightning.py:32-37)
+    and - when /root/reference is present - exactly the reference's state_dict keys and shapes."""
+    import os
+    import sys
+    from gim_b200 import DKMv3
+    m = DKMv3(None, 672, 896, upsample_preds=True)
+    assert (m.h_resized, m.w_resized, m.upsample_preds, m.symmetric, m.sample_mode) == (672, 896, True, True, "threshold_balanced")
+    assert m.upsample_res == (1152, 1536) and m.sample_thresh == 0.05 and m.use_soft_mutual_nearest_neighbours is False
+    m.h_resized, m.w_resized, m.upsample_res = 660, 880, (1152, 1536)   # what the ZEB harness does
+    ref_root = os.environ.get("GIM_REFERENCE_ROOT", "/root/reference")
+    if os.path.isfile(os.path.join(ref_root, "networks", "dkm", "models", "model_zoo", "DKMv3.py")):
+        if ref_root not in sys.path:
+            sys.path.insert(0, ref_root)
+        from networks.dkm.models.model_zoo.DKMv3 import DKMv3 as RefDKMv3
+        ref = RefDKMv3(None, 672, 896, upsample_preds=True).state_dict()
+        ref = {k: v for k, v in ref.items() if "encoder.net.fc" not in k}   # callers strip fc (demo.py:358-363)
+        ours = m.state_dict()
+        assert set(ours) == set(ref)
+        assert all(tuple(ours[k].shape) == tuple(ref[k].shape) for k in ref)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.match(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))
+    with pytest.raises(NotImplementedError):
+        DKMv3(None, 96, 128, symmetric=False).match(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))
+
+
+def test_dkm_blob_layout_and_folding():
+    from gim_b200.dkm import packed_dkm_tensors
+    from gim_b200.dkm_params import seeded_state_dict
+    sd = seeded_state_dict(0)
+    pt = packed_dkm_tensors(sd)
+    assert pt["enc.l4.0.ds.w"].shape == (2048, 1, 1, 1024) and pt["proj.16.w"].shape == (512, 1, 1, 1024)
+    assert pt["ref.16.b0.pw.w"].shape == (1377, 1, 1, 1377) and pt["ref.16.b0.dw_wt"].shape == (25, 1408)
+    assert pt["ref.1.b0.dw_w"].shape == (24, 25) and pt["ref.1.out.w"].shape == (8, 1, 1, 24)       # 3 outputs padded to 8
+    assert torch.equal(pt["ref.1.out.w"][3:], torch.zeros(5, 1, 1, 24)) and torch.equal(pt["ref.1.out.s"], torch.ones(8))
+    # conv bias + BatchNorm folded into one affine: bn(conv(x) + bias) == s * conv(x) + b
+    pre = "decoder.conv_refiner.8.hidden_blocks.2"
+    x = torch.randn(2, 1137, 6, 7)
+    y = torch.nn.functional.conv2d(x, sd[pre + ".0.weight"], sd[pre + ".0.bias"], padding=2, groups=1137)
+    ref = torch.nn.functional.batch_norm(y, sd[pre + ".1.running_mean"], sd[pre + ".1.running_var"], sd[pre + ".1.weight"],
+                                         sd[pre + ".1.bias"], False, 0.0, 1e-5)
+    raw = torch.nn.functional.conv2d(x, sd[pre + ".0.weight"], None, padding=2, groups=1137)
+    folded = raw * pt["ref.8.b3.dw_s"][None, :, None, None] + pt["ref.8.b3.dw_b"][None, :, None, None]
+    assert (ref - folded).abs().max() < 1e-4
+    wt = pt["ref.8.b3.dw_wt"]
+    assert torch.equal(wt[:, :1137], sd[pre + ".0.weight"].reshape(1137, 25).t()) and torch.equal(wt[:, 1137:], torch.zeros(25, wt.shape[1] - 1137))
