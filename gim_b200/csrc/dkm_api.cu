@@ -164,14 +164,16 @@ int encoder(Fwd& F, gimb_dkm* m, const float* nchw, int B, int H, int W, int upt
   Ctx& ctx = F.ctx;
   Arena& A = ctx.arena;
   const int chans[6] = {3, 64, 256, 512, 1024, 2048};
+  // sizes like torchvision's ResNet: every stride-2 stage (7x7 stem, max-pool, 3x3 convs with padding 1) maps n -> ceil(n / 2);
+  // only the stem kernel needs an even input (the ZEB harness runs 660 x 880: 330 -> 165 -> 83 -> 42 -> 21)
+  GIMB_CHECK(H % 2 == 0 && W % 2 == 0, "dkm encoder: the resized image must have even height and width (got %dx%d)", H, W);
   for (int i = 0; i < 6; ++i) {
-    py->C[i] = chans[i]; py->H[i] = H >> i; py->W[i] = W >> i; py->f[i] = nullptr;
+    py->C[i] = chans[i]; py->f[i] = nullptr;
+    py->H[i] = i == 0 ? H : (py->H[i - 1] + 1) / 2;
+    py->W[i] = i == 0 ? W : (py->W[i - 1] + 1) / 2;
   }
   const int top = upto == 8 ? 3 : 5;
-  for (int i = 1; i <= top; ++i) {
-    GIMB_CHECK((py->H[i - 1] % 2 == 0 && py->W[i - 1] % 2 == 0), "dkm encoder: %dx%d is not divisible by %d", H, W, 1 << i);
-    py->f[i] = A.alloc<float>((size_t)B * py->H[i] * py->W[i] * chans[i]);
-  }
+  for (int i = 1; i <= top; ++i) py->f[i] = A.alloc<float>((size_t)B * py->H[i] * py->W[i] * chans[i]);
   py->f[0] = A.alloc<float>((size_t)B * H * W * 4);  // image as NHWC with pitch 4 (refiner "1")
   GIMB_CHECK(ctx.dry || !A.overflow, "dkm encoder: workspace exhausted");
   size_t mark = A.mark();
@@ -184,7 +186,7 @@ int encoder(Fwd& F, gimb_dkm* m, const float* nchw, int B, int H, int W, int upt
   for (int li = 0; li < top - 1; ++li) {
     for (size_t bi = 0; bi < m->layers[li].size(); ++bi) {
       const DBottleneck& b = m->layers[li][bi];
-      const int oH = cH / b.stride, oW = cW / b.stride;
+      const int oH = b.stride == 2 ? (cH + 1) / 2 : cH, oW = b.stride == 2 ? (cW + 1) / 2 : cW;
       const bool last = bi + 1 == m->layers[li].size();
       // block output: planes (next GEMM operand + identity); the last block of a layer also as fp32 (pyramid level)
       ActT xo = F.alloc((size_t)B * oH * oW, b.c3.cout, false, true);
@@ -339,7 +341,8 @@ int conv_refiner(Fwd& F, const Refiner& r, const float* x, const float* y, int l
 struct DecoderOut {
   float* flow1;   // [2, h, w, 2] finest flow
   float* cert1;   // [2, h, w]
-  float* cert16;  // [2, h/16, w/16] (first pass only)
+  float* cert16;  // [2, h16, w16] (first pass only)
+  int h16, w16;
 };
 
 // Decoder.forward (dkm.py:454-534).  f2 = f1 with the two batch halves swapped (forward_symmetric, dkm.py:640-650).
@@ -358,6 +361,7 @@ int decoder(Fwd& F, gimb_dkm* m, const Pyramid& py, const Pyramid& sw, bool upsa
   float* old = A.alloc<float>((size_t)B * py.H[4] * py.W[4] * DFN_DIM * (upsample ? 0 : 1) + 4);
   float* old_n = A.alloc<float>((size_t)B * py.H[4] * py.W[4] * DFN_DIM * (upsample ? 0 : 1) + 4);
   out->cert16 = A.alloc<float>((size_t)B * py.H[4] * py.W[4]);
+  out->h16 = py.H[4]; out->w16 = py.W[4];
   GIMB_CHECK(ctx.dry || !A.overflow, "dkm decoder: workspace exhausted");
   bool have_cert = false;
   if (!upsample) {
@@ -474,8 +478,9 @@ int swapped(Ctx& ctx, const Pyramid& py, Pyramid* sw) {
 int match_impl(Ctx& ctx, gimb_dkm* m, const MatchArgs& a) {
   Arena& A = ctx.arena;
   Fwd F{ctx, m->engine};
-  GIMB_CHECK(a.h % 32 == 0 && a.w % 32 == 0, "gimb_dkm_match: h_resized / w_resized must be multiples of 32 (got %dx%d)", a.h, a.w);
-  GIMB_CHECK(!a.upsample || (a.uh % 8 == 0 && a.uw % 8 == 0), "gimb_dkm_match: upsample_res must be multiples of 8");
+  GIMB_CHECK(a.h >= 32 && a.w >= 32 && a.h % 2 == 0 && a.w % 2 == 0, "gimb_dkm_match: h_resized / w_resized must be even and >= 32 (got %dx%d)",
+             a.h, a.w);
+  GIMB_CHECK(!a.upsample || (a.uh >= 8 && a.uw >= 8 && a.uh % 2 == 0 && a.uw % 2 == 0), "gimb_dkm_match: upsample_res must be even");
   // ---- pass 1 at (h, w)
   float* batch = A.alloc<float>((size_t)2 * 3 * a.h * a.w);
   GIMB_CHECK(ctx.dry || !A.overflow, "gimb_dkm_match: workspace too small");
@@ -510,7 +515,7 @@ int match_impl(Ctx& ctx, gimb_dkm* m, const MatchArgs& a) {
   // low-resolution certainty (scale 16 of pass 1) at the output size (dkm.py:686-693)
   low = A.alloc<float>((size_t)2 * hs * ws);
   GIMB_CHECK(ctx.dry || !A.overflow, "gimb_dkm_match: workspace too small");
-  GIMB_TRY(dkm_resize_nhwc(ctx, d1.cert16, 2, a.h / 16, a.w / 16, 1, 1, low, hs, ws, 1));
+  GIMB_TRY(dkm_resize_nhwc(ctx, d1.cert16, 2, d1.h16, d1.w16, 1, 1, low, hs, ws, 1));
   DkmFinalArgs fa;
   fa.flow = flow; fa.certainty = cert; fa.low_cert = low; fa.im1 = a.im1; fa.im2 = a.im2;
   fa.H1 = a.H1; fa.W1 = a.W1; fa.H2 = a.H2; fa.W2 = a.W2; fa.hs = hs; fa.ws = ws; fa.warp = a.warp; fa.cert_out = a.cert;

@@ -60,7 +60,7 @@ __global__ void resize_nhwc_kernel(const float* __restrict__ in, int B, int H, i
 
 __global__ void maxpool_kernel(const float* __restrict__ in, int B, int H, int W, int C, float* __restrict__ out, __half* hi, __half* lo,
                                int ldp) {
-  const int OH = H / 2, OW = W / 2;
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;  // floor((H + 2 - 3) / 2) + 1
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)B * OH * OW * C;
   if (idx >= total) return;
@@ -743,9 +743,8 @@ int dkm_resize_nhwc(Ctx& ctx, const float* in, int B, int H, int W, int C, int l
   GIMB_DKM_LAUNCH_END();
 }
 int dkm_maxpool3x3s2(Ctx& ctx, const float* in, int B, int H, int W, int C, float* out, const SplitPlanes* planes) {
-  GIMB_CHECK(H % 2 == 0 && W % 2 == 0, "dkm_maxpool3x3s2: even input size expected");
   if (ctx.dry) return 0;
-  const long long n = (long long)B * (H / 2) * (W / 2) * C;
+  const long long n = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * C;
   maxpool_kernel<<<blocks(n, 256), 256, 0, ctx.stream>>>(in, B, H, W, C, out, planes ? planes->hi : nullptr, planes ? planes->lo : nullptr,
                                                          planes ? planes->ld : 0);
   GIMB_DKM_LAUNCH_END();

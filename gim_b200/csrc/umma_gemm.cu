@@ -1095,7 +1095,7 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     GIMB_TRY(rows_map(&maps.b_hi, g.b.hi, Kw, g.N, g.b.ld, p.bn, 1, bkk));
   } else {
     GIMB_CHECK(g.K2 == 0, "umma_gemm: concat only in row mode");
-    GIMB_CHECK(g.stride == 1 || (g.H % 2 == 0 && g.W % 2 == 0), "umma_gemm: stride-2 needs even H, W");
+    // stride 2 with odd H / W is fine: the four parity views get their own extents below
     p.OH = g.OH; p.OW = g.OW;
     p.tiles_h = cdiv(g.OH, TH); p.tiles_w = cdiv(g.OW, TW);
     p.tiles_per_img = p.tiles_h * p.tiles_w;
@@ -1109,7 +1109,10 @@ int umma_gemm(Ctx& ctx, const UmmaGemm& g) {
     for (int v = 0; v < nviews; ++v) {
       const int py = v >> 1, px = v & 1;
       const uint64_t s = g.stride;
-      uint64_t dims[4] = {(uint64_t)g.K1, (uint64_t)g.W / s, (uint64_t)g.H / s, (uint64_t)g.B};
+      // view (py, px) holds the pixels (2y' + py, 2x' + px): (H + 1 - py) / 2 rows, (W + 1 - px) / 2 columns (odd sizes: the
+      // views differ by one); everything outside is zero-filled = the convolution's padding
+      uint64_t dims[4] = {(uint64_t)g.K1, (uint64_t)(g.stride == 2 ? (g.W + 1 - px) / 2 : g.W),
+                          (uint64_t)(g.stride == 2 ? (g.H + 1 - py) / 2 : g.H), (uint64_t)g.B};
       uint64_t strides[3] = {s * ld * 2, s * (uint64_t)g.W * ld * 2, (uint64_t)g.H * g.W * ld * 2};
       uint32_t box[4] = {(uint32_t)bkk, TW, TH, 1};
       const size_t off = ((size_t)py * g.W + px) * ld;

@@ -210,7 +210,10 @@ class RegressionMatcher(DKMParams):
                 taps = _Taps()
                 for name in self.debug_taps:
                     if name in ("dfn_flow16", "refiner_in16", "refiner_dw16", "refiner_pw16", "refiner_out16"):
-                        t = torch.zeros(2, h // 16, w // 16, 2 if name == "dfn_flow16" else 1377, device=im1.device)
+                        h16, w16 = h, w
+                        for _ in range(4):
+                            h16, w16 = (h16 + 1) // 2, (w16 + 1) // 2
+                        t = torch.zeros(2, h16, w16, 2 if name == "dfn_flow16" else 1377, device=im1.device)
                         setattr(taps, name, t.data_ptr())
                         self.last_taps[name] = t
                         continue
@@ -218,8 +221,9 @@ class RegressionMatcher(DKMParams):
                     digits = "".join(ch for ch in name if ch.isdigit())
                     s = int(digits).bit_length() - 1 if digits else 0
                     upass = name.endswith("u")
-                    hh, ww = ((uh, uw) if upass else (h, w))
-                    hs, ws = hh >> s, ww >> s
+                    hs, ws = ((uh, uw) if upass else (h, w))
+                    for _ in range(s):                       # every stride-2 stage maps n -> ceil(n / 2)
+                        hs, ws = (hs + 1) // 2, (ws + 1) // 2
                     if kind == "enc":
                         t = torch.zeros(2, hs, ws, (3, 64, 256, 512, 1024, 2048)[s], device=im1.device)
                         taps.enc[s] = t.data_ptr()

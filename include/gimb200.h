@@ -196,8 +196,9 @@ void gimb_dkm_destroy(gimb_dkm* h);
 int gimb_dkm_set_engine(gimb_dkm* h, int engine);
 uint64_t gimb_dkm_launch_count(gimb_dkm* h);
 /* Bytes of device workspace one match() call needs.  im1 is [3, H1, W1], im2 [3, H2, W2]; (h_resized, w_resized) are the
- * caller-overwritable attributes of the reference object (trainer/lightning.py:32-37), multiples of 32; when
- * upsample_preds != 0 the second pass runs at (up_h, up_w) (multiples of 8). */
+ * caller-overwritable attributes of the reference object (trainer/lightning.py:32-37; the ZEB harness sets 660 x 880), even;
+ * when upsample_preds != 0 the second pass runs at (up_h, up_w) (even).  Every stride-2 stage maps n -> ceil(n / 2) like
+ * torchvision's ResNet. */
 int gimb_dkm_workspace_bytes(gimb_dkm* h, int H1, int W1, int H2, int W2, int h_resized, int w_resized,
                              int upsample_preds, int up_h, int up_w, size_t* bytes);
 /* match(): DEVICE fp32 NCHW images in [0, 1]; outputs warp [Hout, 2*Wout, 4] and certainty [Hout, 2*Wout] with

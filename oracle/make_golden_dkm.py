@@ -20,6 +20,9 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 CASES = {  # name: (input h, w, h_resized, w_resized, upsample_res, synth pair index)
     "dkm_64x96_up128x192": (80, 112, 64, 96, (128, 192), 3),
     "dkm_96x128_up192x256": (120, 160, 96, 128, (192, 256), 5),
+    # sizes that are NOT multiples of 32 (the ZEB harness runs 660 x 880, trainer/lightning.py:33-34): 88 -> 44 -> 22 -> 11 -> 6 -> 3
+    # and 120 -> 60 -> 30 -> 15 -> 8 -> 4, i.e. stride-2 convolutions on odd maps; second pass 180 x 244 -> 90 x 122 -> 45 x 61 -> 23 x 31
+    "dkm_odd_88x120_up180x244": (100, 140, 88, 120, (180, 244), 9),
     # big enough for the tensor-core Gram path of the GP (N = 14 * 18 = 252 tokens at 1/16) and several Cholesky blocks
     "dkm_224x288_up320x416": (240, 320, 224, 288, (320, 416), 7),
     # BASELINE config 3 geometry (672x896 -> 1152x1536 second pass): outputs stored on a stride-8 grid (the full tensors

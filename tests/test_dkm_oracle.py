@@ -9,7 +9,7 @@ import torch
 from gim_b200.dkm_params import seeded_state_dict
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-DKM_CASES = ["dkm_64x96_up128x192", "dkm_96x128_up192x256", "dkm_224x288_up320x416"]
+DKM_CASES = ["dkm_64x96_up128x192", "dkm_96x128_up192x256", "dkm_odd_88x120_up180x244", "dkm_224x288_up320x416"]
 DKM_BIG_CASES = ["dkm_672x896_up1152x1536_s8"]  # outputs stored on a stride-8 grid
 # dense outputs in normalised [-1, 1] coordinates / probabilities; north_star tolerance 1e-3 abs
 TOL_WARP, TOL_CERT = 1e-3, 1e-3
