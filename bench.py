@@ -140,6 +140,39 @@ def cpu_reference_pairs_per_sec(n_calls, warmup, first=0):
     return 1.0 / med, med, M, torch.get_num_threads()
 
 
+def run_reference_dkm(args):
+    """CPU arm of config 3: the oracle port of DKMv3.match (pinned bit for bit to the unmodified reference at small sizes) on
+    the host cores.  Bounded sample: one pair at 224x288 -> 384x512 per step (1/9 of the pixels of the 672x896 workload),
+    reported scaled by the pixel ratio and labelled as such."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from gim_b200 import synth
+    from gim_b200.dkm_params import seeded_state_dict
+    from oracle import dkm_oracle
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
+    sd = seeded_state_dict(0)
+    a, b = synth.make_pairs(1, 672, 896, first=0)
+    steps_run, warm_run = min(max(1, args.steps), 3), min(max(0, args.warmup), 1)
+    ts = []
+    with torch.no_grad():
+        for i in range(warm_run + steps_run):
+            t0 = time.perf_counter()
+            dkm_oracle.match(sd, a, b, 224, 288, (384, 512))
+            if i >= warm_run:
+                ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2] * 9.0
+    sample = (f"oracle/dkm_oracle.py, 1 pair per step at 224x288 -> 384x512, {steps_run} timed + {warm_run} warm-up calls, median x 9 "
+              f"(pixel ratio to 672x896 -> 1152x1536)")
+    line = {"impl": "reference", "metric": "image-pairs/sec @672x896 gim_dkm", "value": 1.0 / med, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": steps_run, "warmup": warm_run, "requested_steps": args.steps, "requested_warmup": args.warmup, "ms_per_step": med * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic (seeded random weights)",
+            "config": {"workload": f"gim_dkm 672x896 batch-{args.batch} synthetic pairs", "device": "cpu"},
+            "cpu_baseline": {"value": 1.0 / med, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": 1.0 / med, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -469,8 +502,8 @@ def main():
     args = ap.parse_args()
     if args.batch is None:
         args.batch = 8 if args.workload == "dkm" else 32
-    if args.workload == "dkm" and args.impl == "ours":
-        return run_dkm(args)
+    if args.workload == "dkm":
+        return run_dkm(args) if args.impl == "ours" else run_reference_dkm(args)
     if args.impl == "reference":
         run_reference(args)
     else:

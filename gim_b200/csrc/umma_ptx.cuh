@@ -4,6 +4,9 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -230,8 +233,34 @@ int get_encode(EncodeTiledFn* out) {
 
 // fp16 tensor map, SWIZZLE_64B, inner box = 32 elements (64 B).  dims/strides innermost first; strides in BYTES for
 // dims 1.. (rank-1 entries).
+// Encoded tensor maps are a pure function of (address, extents, strides, box, type): a forward re-creates the same ~1500
+// descriptors every call (same workspace layout for the same shapes), so they are cached per host thread.
+struct TMapKey {
+  uint64_t v[15];
+  bool operator==(const TMapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TMapKeyHash {
+  size_t operator()(const TMapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 15; ++i) { h ^= k.v[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+
 int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
              const uint32_t* box, bool f32 = false) {
+  static thread_local std::unordered_map<TMapKey, CUtensorMap, TMapKeyHash> cache;
+  TMapKey key;
+  memset(&key, 0, sizeof(key));
+  key.v[0] = (uint64_t)(uintptr_t)ptr;
+  key.v[1] = (uint64_t)rank | (f32 ? 1ull << 32 : 0ull);
+  for (int i = 0; i < rank; ++i) { key.v[2 + i] = dims[i]; key.v[10 + i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.v[6 + i] = strides_bytes[i];
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *m = it->second;
+    return 0;
+  }
   EncodeTiledFn enc;
   GIMB_TRY(get_encode(&enc));
   cuuint64_t gd[5];
@@ -249,6 +278,8 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, co
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GIMB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rank %d, dims %llu %llu %llu)", (int)r, rank,
              (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)(rank > 2 ? gd[2] : 0));
+  if (cache.size() >= 65536) cache.clear();  // bound the memory of long-running processes that see many shapes
+  cache.emplace(key, *m);
   return 0;
 }
 
