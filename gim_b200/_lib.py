@@ -44,6 +44,11 @@ EXPORTS = {
                                            c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_size_t,
                                            POINTER(LoftrOut), POINTER(LoftrOut), POINTER(c_int64), POINTER(c_uint64),
                                            POINTER(c_uint64), c_void_p]),
+    "gimb_loftr_stage_host_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                         c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, POINTER(c_uint64), c_void_p]),
+    "gimb_loftr_forward_staged_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_size_t, c_void_p, c_size_t, POINTER(LoftrOut), POINTER(LoftrOut),
+                                             POINTER(c_int64), POINTER(c_uint64), c_void_p]),
     "gimb_loftr_launch_count": (c_uint64, [c_void_p]),
     "gimb_loftr_corr_fallbacks": (c_uint64, [c_void_p]),
     "gimb_loftr_set_profiling": (c_int, [c_void_p, c_int]),

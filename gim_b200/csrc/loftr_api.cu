@@ -658,12 +658,40 @@ int gimb_loftr_host_u8_staging_bytes(int n, int ih0, int iw0, int ih1, int iw1, 
   return 0;
 }
 
-int gimb_loftr_forward_host_u8(gimb_loftr* h, const uint8_t* img0, int ih0, int iw0, const uint8_t* img1, int ih1, int iw1,
-                               const float* scale0, const float* scale1, int n, int h0, int w0, int h1, int w1, void* dev_inputs,
-                               size_t dev_inputs_bytes, void* workspace, size_t workspace_bytes, const gimb_loftr_out* dev_out,
-                               const gimb_loftr_out* host_out, int64_t* m_out, uint64_t* h2d_bytes, uint64_t* d2h_bytes,
-                               void* stream) {
-  GIMB_CHECK(h && img0 && img1 && dev_inputs && dev_out && host_out && m_out, "gimb_loftr_forward_host_u8: null argument");
+namespace {
+// Layout of the u8 staging buffer (gimb_loftr_host_u8_staging_bytes): raw bytes, converted fp32 NCHW, masks, scales.
+struct U8Staging {
+  uint8_t *u0, *u1, *m0, *m1;
+  float *c0, *c1, *s0, *s1;
+  size_t b0, b1;
+  bool padded;
+};
+U8Staging carve_u8_staging(void* dev_inputs, int n, int ih0, int iw0, int ih1, int iw1, int h0, int w0, int h1, int w1, bool with_scale) {
+  char* p = (char*)(((uintptr_t)dev_inputs + 255) / 256 * 256);
+  auto carve = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
+  U8Staging s;
+  s.b0 = (size_t)n * ih0 * iw0 * 3;
+  s.b1 = (size_t)n * ih1 * iw1 * 3;
+  s.u0 = (uint8_t*)carve(s.b0);
+  s.u1 = (uint8_t*)carve(s.b1);
+  s.c0 = (float*)carve((size_t)n * 3 * h0 * w0 * 4);
+  s.c1 = (float*)carve((size_t)n * 3 * h1 * w1 * 4);
+  s.padded = ih0 != h0 || iw0 != w0 || ih1 != h1 || iw1 != w1;  // the loader returns a mask only when it pads
+  s.m0 = (uint8_t*)carve((size_t)n * (h0 / 8) * (w0 / 8));
+  s.m1 = (uint8_t*)carve((size_t)n * (h1 / 8) * (w1 / 8));
+  s.s0 = s.s1 = nullptr;
+  if (with_scale) {
+    s.s0 = (float*)carve((size_t)n * 8);
+    s.s1 = (float*)carve((size_t)n * 8);
+  }
+  return s;
+}
+}  // namespace
+
+int gimb_loftr_stage_host_u8(gimb_loftr* h, const uint8_t* img0, int ih0, int iw0, const uint8_t* img1, int ih1, int iw1,
+                             const float* scale0, const float* scale1, int n, int h0, int w0, int h1, int w1, void* dev_inputs,
+                             size_t dev_inputs_bytes, uint64_t* h2d_bytes, void* stream) {
+  GIMB_CHECK(h && img0 && img1 && dev_inputs, "gimb_loftr_stage_host_u8: null argument");
   GIMB_CHECK((scale0 == nullptr) == (scale1 == nullptr), "scale0/scale1 go together");
   size_t need = 0;
   GIMB_TRY(gimb_loftr_host_u8_staging_bytes(n, ih0, iw0, ih1, iw1, h0, w0, h1, w1, scale0 != nullptr, &need));
@@ -671,41 +699,41 @@ int gimb_loftr_forward_host_u8(gimb_loftr* h, const uint8_t* img0, int ih0, int 
   DeviceGuard guard(h->device);
   GIMB_CHECK(guard.ok, "cudaSetDevice(%d) failed", h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  char* p = (char*)(((uintptr_t)dev_inputs + 255) / 256 * 256);
-  uint64_t up = 0;
-  auto carve = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
-  const size_t b0 = (size_t)n * ih0 * iw0 * 3, b1 = (size_t)n * ih1 * iw1 * 3;
-  uint8_t* d_u0 = (uint8_t*)carve(b0);
-  uint8_t* d_u1 = (uint8_t*)carve(b1);
-  float* d_c0 = (float*)carve((size_t)n * 3 * h0 * w0 * 4);
-  float* d_c1 = (float*)carve((size_t)n * 3 * h1 * w1 * 4);
-  const bool padded = ih0 != h0 || iw0 != w0 || ih1 != h1 || iw1 != w1;  // the loader returns a mask only when it pads
-  uint8_t* d_m0 = (uint8_t*)carve((size_t)n * (h0 / 8) * (w0 / 8));
-  uint8_t* d_m1 = (uint8_t*)carve((size_t)n * (h1 / 8) * (w1 / 8));
-  GIMB_CUDA(cudaMemcpyAsync(d_u0, img0, b0, cudaMemcpyHostToDevice, st));
-  GIMB_CUDA(cudaMemcpyAsync(d_u1, img1, b1, cudaMemcpyHostToDevice, st));
-  up += b0 + b1;
-  const float *d_s0 = nullptr, *d_s1 = nullptr;
+  const U8Staging s = carve_u8_staging(dev_inputs, n, ih0, iw0, ih1, iw1, h0, w0, h1, w1, scale0 != nullptr);
+  uint64_t up = s.b0 + s.b1;
+  GIMB_CUDA(cudaMemcpyAsync(s.u0, img0, s.b0, cudaMemcpyHostToDevice, st));
+  GIMB_CUDA(cudaMemcpyAsync(s.u1, img1, s.b1, cudaMemcpyHostToDevice, st));
   if (scale0) {
-    float* s0 = (float*)carve((size_t)n * 8);
-    float* s1 = (float*)carve((size_t)n * 8);
-    GIMB_CUDA(cudaMemcpyAsync(s0, scale0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    GIMB_CUDA(cudaMemcpyAsync(s1, scale1, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    d_s0 = s0; d_s1 = s1;
+    GIMB_CUDA(cudaMemcpyAsync(s.s0, scale0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    GIMB_CUDA(cudaMemcpyAsync(s.s1, scale1, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     up += (uint64_t)n * 16;
   }
-  {
-    const long long t0 = (long long)n * 3 * h0 * w0, t1 = (long long)n * 3 * h1 * w1;
-    u8_to_nchw_kernel<<<(unsigned)((t0 + 255) / 256), 256, 0, st>>>(d_u0, n, ih0, iw0, d_c0, h0, w0);
-    u8_to_nchw_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, st>>>(d_u1, n, ih1, iw1, d_c1, h1, w1);
-    if (padded) {
-      pad_mask_kernel<<<(n * (h0 / 8) * (w0 / 8) + 255) / 256, 256, 0, st>>>(d_m0, n, h0 / 8, w0 / 8, ih0, iw0);
-      pad_mask_kernel<<<(n * (h1 / 8) * (w1 / 8) + 255) / 256, 256, 0, st>>>(d_m1, n, h1 / 8, w1 / 8, ih1, iw1);
-    }
-    GIMB_LAUNCH_CHECK();
-    h->launches += padded ? 4 : 2;
+  const long long t0 = (long long)n * 3 * h0 * w0, t1 = (long long)n * 3 * h1 * w1;
+  u8_to_nchw_kernel<<<(unsigned)((t0 + 255) / 256), 256, 0, st>>>(s.u0, n, ih0, iw0, s.c0, h0, w0);
+  u8_to_nchw_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, st>>>(s.u1, n, ih1, iw1, s.c1, h1, w1);
+  if (s.padded) {
+    pad_mask_kernel<<<(n * (h0 / 8) * (w0 / 8) + 255) / 256, 256, 0, st>>>(s.m0, n, h0 / 8, w0 / 8, ih0, iw0);
+    pad_mask_kernel<<<(n * (h1 / 8) * (w1 / 8) + 255) / 256, 256, 0, st>>>(s.m1, n, h1 / 8, w1 / 8, ih1, iw1);
   }
-  GIMB_TRY(gimb_loftr_forward(h, d_c0, d_c1, padded ? d_m0 : nullptr, padded ? d_m1 : nullptr, d_s0, d_s1, n, h0, w0, h1, w1,
+  GIMB_LAUNCH_CHECK();
+  h->launches += s.padded ? 4 : 2;
+  if (h2d_bytes) *h2d_bytes = up;
+  return 0;
+}
+
+int gimb_loftr_forward_staged_u8(gimb_loftr* h, int ih0, int iw0, int ih1, int iw1, int with_scale, int n, int h0, int w0, int h1,
+                                 int w1, void* dev_inputs, size_t dev_inputs_bytes, void* workspace, size_t workspace_bytes,
+                                 const gimb_loftr_out* dev_out, const gimb_loftr_out* host_out, int64_t* m_out,
+                                 uint64_t* d2h_bytes, void* stream) {
+  GIMB_CHECK(h && dev_inputs && dev_out && host_out && m_out, "gimb_loftr_forward_staged_u8: null argument");
+  size_t need = 0;
+  GIMB_TRY(gimb_loftr_host_u8_staging_bytes(n, ih0, iw0, ih1, iw1, h0, w0, h1, w1, with_scale, &need));
+  GIMB_CHECK(dev_inputs_bytes >= need, "dev_inputs too small: %zu < %zu", dev_inputs_bytes, need);
+  DeviceGuard guard(h->device);
+  GIMB_CHECK(guard.ok, "cudaSetDevice(%d) failed", h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const U8Staging s = carve_u8_staging(dev_inputs, n, ih0, iw0, ih1, iw1, h0, w0, h1, w1, with_scale != 0);
+  GIMB_TRY(gimb_loftr_forward(h, s.c0, s.c1, s.padded ? s.m0 : nullptr, s.padded ? s.m1 : nullptr, s.s0, s.s1, n, h0, w0, h1, w1,
                               workspace, workspace_bytes, dev_out, nullptr, m_out, stream));
   const int64_t M = *m_out;
   GIMB_CHECK(M <= host_out->capacity, "host_out capacity %lld < M = %lld", (long long)host_out->capacity, (long long)M);
@@ -726,9 +754,20 @@ int gimb_loftr_forward_host_u8(gimb_loftr* h, const uint8_t* img0, int ih0, int 
   GIMB_TRY(pull(host_out->mkpts1_f, dev_out->mkpts1_f, M * 8));
   GIMB_TRY(pull(host_out->expec_f, dev_out->expec_f, M * 12));
   GIMB_CUDA(cudaStreamSynchronize(st));
-  if (h2d_bytes) *h2d_bytes = up;
   if (d2h_bytes) *d2h_bytes = down;
   return 0;
+}
+
+int gimb_loftr_forward_host_u8(gimb_loftr* h, const uint8_t* img0, int ih0, int iw0, const uint8_t* img1, int ih1, int iw1,
+                               const float* scale0, const float* scale1, int n, int h0, int w0, int h1, int w1, void* dev_inputs,
+                               size_t dev_inputs_bytes, void* workspace, size_t workspace_bytes, const gimb_loftr_out* dev_out,
+                               const gimb_loftr_out* host_out, int64_t* m_out, uint64_t* h2d_bytes, uint64_t* d2h_bytes,
+                               void* stream) {
+  GIMB_CHECK(h && img0 && img1 && dev_inputs && dev_out && host_out && m_out, "gimb_loftr_forward_host_u8: null argument");
+  GIMB_TRY(gimb_loftr_stage_host_u8(h, img0, ih0, iw0, img1, ih1, iw1, scale0, scale1, n, h0, w0, h1, w1, dev_inputs, dev_inputs_bytes,
+                                    h2d_bytes, stream));
+  return gimb_loftr_forward_staged_u8(h, ih0, iw0, ih1, iw1, scale0 != nullptr, n, h0, w0, h1, w1, dev_inputs, dev_inputs_bytes, workspace,
+                                      workspace_bytes, dev_out, host_out, m_out, d2h_bytes, stream);
 }
 
 uint64_t gimb_loftr_launch_count(gimb_loftr* h) { return h ? h->launches : 0; }

@@ -85,6 +85,20 @@ class _Transformer(nn.Module):
 
 
 # ----------------------------------------------------------------------------- the module
+class StagedU8:
+    """One batch whose upload + device-side pre-processing has been enqueued by LoFTR.stage_u8: the device staging buffer,
+    the event that marks it ready, its geometry, and references that keep the host tensors alive until the forward ran."""
+
+    def __init__(self, buf, ready, geometry, with_scale, h2d_bytes, keep):
+        self.buf, self.ready, self.geometry, self.with_scale, self.h2d_bytes, self._keep = buf, ready, geometry, with_scale, h2d_bytes, keep
+
+    def release(self):
+        if self.buf is not None:
+            self.buf._gimb_busy = False
+        self.buf = None
+        self._keep = None
+
+
 class LoFTR(nn.Module):
     def __init__(self, config=None):
         super().__init__()
@@ -101,6 +115,8 @@ class LoFTR(nn.Module):
         self._workspace = None
         self._staging = None
         self._host_out = None
+        self._copy_stream = None
+        self._stage_pool = []
         self.last_h2d_bytes = 0
         self.last_d2h_bytes = 0
         for p in self.parameters():
@@ -319,16 +335,7 @@ class LoFTR(nn.Module):
         if taps:
             data["_taps"] = {k: (v[:M] if k.startswith("fine_win") else v) for k, v in tap_tensors.items()}
 
-    @torch.no_grad()
-    def forward_u8(self, data):
-        """GPU pre-processing entry (SURVEY 8 f.1, `gimb_loftr_forward_host_u8`): `data['color0_u8'|'color1_u8']` are
-        CPU uint8 RGB tensors [N, h, w, 3] as cv2 delivers them (after the loader's cv2.resize, datasets/utils.py:108);
-        the float conversion (/255), HWC -> CHW, the zero padding to `data['pad0'|'pad1']` = (H, W) (default: the image
-        size, which must then be a multiple of 8) and the 1/8 padding masks happen on the device.  Optional
-        `scale0/scale1` [N, 2].  Results come back as CPU tensors under the same keys as forward()."""
-        self._ensure_handle()
-        lib = _lib.load()
-        dev = self._device()
+    def _u8_geometry(self, data):
         u0, u1 = data["color0_u8"], data["color1_u8"]
         if u0.dtype != torch.uint8 or u1.dtype != torch.uint8 or u0.dim() != 4 or u1.dim() != 4 or u0.shape[3] != 3 or \
                 u1.shape[3] != 3 or u0.shape[0] != u1.shape[0] or u0.device.type != "cpu" or u1.device.type != "cpu":
@@ -340,36 +347,96 @@ class LoFTR(nn.Module):
         h1, w1 = data.get("pad1", (ih1, iw1))
         if any(v % 8 for v in (h0, w0, h1, w1)):
             raise RuntimeError(f"padded image sizes must be multiples of 8, got {h0}x{w0}, {h1}x{w1}")
-        has_scale = "scale0" in data
         s0 = s1 = None
-        if has_scale:
+        if "scale0" in data:
             s0, s1 = data["scale0"].to(torch.float32).contiguous().cpu(), data["scale1"].to(torch.float32).contiguous().cpu()
+        return u0, u1, s0, s1, (n, ih0, iw0, ih1, iw1, h0, w0, h1, w1)
+
+    @torch.no_grad()
+    def stage_u8(self, data, stream=None):
+        """First half of forward_u8 (`gimb_loftr_stage_host_u8`): enqueue the upload and the device-side pre-processing of one
+        batch on `stream` (default: a copy stream owned by the model) and return a StagedU8 WITHOUT waiting, so that the
+        upload of batch i+1 overlaps the forward of batch i.  Pass the result as `data['staged']` to forward_u8.  The uint8
+        host tensors should be pinned (a pageable copy is synchronous) and must not change until the forward ran."""
+        self._ensure_handle()
+        lib = _lib.load()
+        dev = self._device()
+        u0, u1, s0, s1, geo = self._u8_geometry(data)
+        n, ih0, iw0, ih1, iw1, h0, w0, h1, w1 = geo
+        with torch.cuda.device(dev):
+            need = ctypes.c_size_t()
+            _lib.check(lib.gimb_loftr_host_u8_staging_bytes(n, ih0, iw0, ih1, iw1, h0, w0, h1, w1, int(s0 is not None), ctypes.byref(need)))
+            cur = torch.cuda.current_stream(dev)
+            if stream is None:
+                if self._copy_stream is None or self._copy_stream.device != dev:
+                    self._copy_stream = torch.cuda.Stream(dev)
+                stream = self._copy_stream
+            # staging buffers are kept by the model and recycled once their forward ran (allocating ~300 MB per call through
+            # the caching allocator with a cross-stream dependency costs a cudaMalloc per step)
+            buf = None
+            for cand in self._stage_pool:
+                if cand.device == dev and cand.numel() >= need.value and not getattr(cand, "_gimb_busy", False):
+                    buf = cand
+                    break
+            if buf is None:
+                self._stage_pool = [c for c in self._stage_pool if getattr(c, "_gimb_busy", False)][-3:]
+                buf = torch.empty(need.value, dtype=torch.uint8, device=dev)
+                self._stage_pool.append(buf)
+                if stream != cur:
+                    buf.record_stream(stream)
+            buf._gimb_busy = True
+            if stream != cur:
+                stream.wait_stream(cur)      # the previous consumer of this buffer ran on the compute stream
+            up = ctypes.c_uint64()
+            ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+            _lib.check(lib.gimb_loftr_stage_host_u8(self._handle, u0.data_ptr(), ih0, iw0, u1.data_ptr(), ih1, iw1, ptr(s0), ptr(s1),
+                                                    n, h0, w0, h1, w1, buf.data_ptr(), buf.numel(), ctypes.byref(up), stream.cuda_stream))
+            ready = torch.cuda.Event()
+            ready.record(stream)
+        return StagedU8(buf, ready, geo, s0 is not None, up.value, (u0, u1, s0, s1))
+
+    @torch.no_grad()
+    def forward_u8(self, data):
+        """GPU pre-processing entry (SURVEY 8 f.1, `gimb_loftr_forward_host_u8`): `data['color0_u8'|'color1_u8']` are
+        CPU uint8 RGB tensors [N, h, w, 3] as cv2 delivers them (after the loader's cv2.resize, datasets/utils.py:108);
+        the float conversion (/255), HWC -> CHW, the zero padding to `data['pad0'|'pad1']` = (H, W) (default: the image
+        size, which must then be a multiple of 8) and the 1/8 padding masks happen on the device.  Optional
+        `scale0/scale1` [N, 2].  Results come back as CPU tensors under the same keys as forward().
+        With `data['staged']` = the result of stage_u8() the upload has already been enqueued (possibly on another stream)
+        and only the forward + read-back run here."""
+        self._ensure_handle()
+        lib = _lib.load()
+        dev = self._device()
+        staged = data.get("staged")
+        if staged is None:
+            staged = self.stage_u8(data, stream=torch.cuda.current_stream(dev))
+        elif staged.buf is None:
+            raise RuntimeError("forward_u8: this staged batch has already been consumed")
+        n, ih0, iw0, ih1, iw1, h0, w0, h1, w1 = staged.geometry
         hc0, wc0, hc1, wc1 = h0 // 8, w0 // 8, h1 // 8, w1 // 8
         self._ensure_pe(hc0, wc0)
         self._ensure_pe(hc1, wc1)
         with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(staged.ready)
             ws = self._ensure_workspace(n, h0, w0, h1, w1, dev)
             cap = n * min(hc0 * wc0, hc1 * wc1)
             outs = self._alloc_outputs(cap, dev)
             o = self._out_struct(cap, outs)
-            need = ctypes.c_size_t()
-            _lib.check(lib.gimb_loftr_host_u8_staging_bytes(n, ih0, iw0, ih1, iw1, h0, w0, h1, w1, int(has_scale), ctypes.byref(need)))
-            if self._staging is None or self._staging.numel() < need.value or self._staging.device != dev:
-                self._staging = torch.empty(need.value, dtype=torch.uint8, device=dev)
+            # persistent pinned read-back buffers (pinning ~10 MB per call costs tens of ms); the results are cloned out of them
             if self._host_out is None or self._host_out["b_ids"].shape[0] < cap:
                 self._host_out = self._alloc_outputs(cap, torch.device("cpu"), pin=True)
             houts = self._host_out
             ho = self._out_struct(houts["b_ids"].shape[0], houts)
-            up, down, m_out = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int64()
-            ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
-            _lib.check(lib.gimb_loftr_forward_host_u8(self._handle, u0.data_ptr(), ih0, iw0, u1.data_ptr(), ih1, iw1, ptr(s0), ptr(s1),
-                                                      n, h0, w0, h1, w1, self._staging.data_ptr(), self._staging.numel(),
-                                                      ws.data_ptr(), ws.numel(), ctypes.byref(o), ctypes.byref(ho),
-                                                      ctypes.byref(m_out), ctypes.byref(up), ctypes.byref(down),
-                                                      torch.cuda.current_stream(dev).cuda_stream))
+            down, m_out = ctypes.c_uint64(), ctypes.c_int64()
+            _lib.check(lib.gimb_loftr_forward_staged_u8(self._handle, ih0, iw0, ih1, iw1, int(staged.with_scale), n, h0, w0, h1, w1,
+                                                        staged.buf.data_ptr(), staged.buf.numel(), ws.data_ptr(), ws.numel(),
+                                                        ctypes.byref(o), ctypes.byref(ho), ctypes.byref(m_out), ctypes.byref(down),
+                                                        cur.cuda_stream))
             M = m_out.value
-            self.last_h2d_bytes, self.last_d2h_bytes = up.value, down.value
+            self.last_h2d_bytes, self.last_d2h_bytes = staged.h2d_bytes, down.value
             res = {k: v[:M].clone() for k, v in houts.items()}
+        staged.release()
         data.update({
             "bs": n, "hw0_i": torch.Size((h0, w0)), "hw1_i": torch.Size((h1, w1)),
             "hw0_c": torch.Size((hc0, wc0)), "hw1_c": torch.Size((hc1, wc1)),

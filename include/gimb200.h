@@ -153,6 +153,21 @@ int gimb_loftr_forward_host_u8(gimb_loftr* h, const uint8_t* img0, int ih0, int 
                                const gimb_loftr_out* host_out, int64_t* m_out, uint64_t* h2d_bytes,
                                uint64_t* d2h_bytes, void* stream);
 
+/* The same in two halves, for callers that overlap the upload of the next batch with the forward of the current one (what a
+ * DataLoader with pin_memory + non_blocking copies does around the reference's forward): gimb_loftr_stage_host_u8 enqueues
+ * the H2D copies and the device-side conversion / padding / masks of one batch on `stream` and returns WITHOUT synchronising
+ * (the host buffers must stay valid and unchanged until that work has run); gimb_loftr_forward_staged_u8 runs the forward
+ * from a staged buffer and reads the results back (one synchronisation at the end, like gimb_loftr_forward_host).  The caller
+ * orders the two (same stream, or an event between a copy stream and the compute stream).
+ * gimb_loftr_forward_host_u8 == stage + forward_staged on one stream. */
+int gimb_loftr_stage_host_u8(gimb_loftr* h, const uint8_t* img0, int ih0, int iw0, const uint8_t* img1, int ih1,
+                             int iw1, const float* scale0, const float* scale1, int n, int h0, int w0, int h1,
+                             int w1, void* dev_inputs, size_t dev_inputs_bytes, uint64_t* h2d_bytes, void* stream);
+int gimb_loftr_forward_staged_u8(gimb_loftr* h, int ih0, int iw0, int ih1, int iw1, int with_scale, int n, int h0,
+                                 int w0, int h1, int w1, void* dev_inputs, size_t dev_inputs_bytes,
+                                 void* workspace, size_t workspace_bytes, const gimb_loftr_out* dev_out,
+                                 const gimb_loftr_out* host_out, int64_t* m_out, uint64_t* d2h_bytes, void* stream);
+
 /* Number of kernels this library launched on behalf of handle `h` since creation (for bench.py's
  * `gpu_launches`), and the per-stage device time of the last forward when profiling is enabled. */
 uint64_t gimb_loftr_launch_count(gimb_loftr* h);

@@ -203,6 +203,30 @@ def test_u8_entry_matches_float_entry_and_masks(model):
     assert d2["b_ids"].numel() > 100
 
 
+def test_staged_u8_uploads_overlap_and_match(model):
+    """stage_u8 (upload + pre-processing on the model's copy stream, no wait) then forward_u8(staged=...): two batches staged
+    ahead of their forwards give the same results as the one-call entry; a staged batch cannot be consumed twice."""
+    import numpy as np
+    z = np.load("tests/golden/small_b2_240x320.npz")
+    u0 = torch.from_numpy(z["color0_u8"]).permute(0, 2, 3, 1).contiguous().pin_memory()
+    u1 = torch.from_numpy(z["color1_u8"]).permute(0, 2, 3, 1).contiguous().pin_memory()
+    _, gold = load_case("small_b2_240x320")
+    s_a = model.stage_u8({"color0_u8": u0, "color1_u8": u1})
+    s_b = model.stage_u8({"color0_u8": u1, "color1_u8": u0, "pad0": (320, 320), "pad1": (320, 320)})   # swapped + padded
+    d_a = {"staged": s_a}
+    model.forward_u8(d_a)
+    assert_matches_equal(d_a, gold, what="staged u8 vs golden: ")
+    d_b = {"staged": s_b}
+    model.forward_u8(d_b)
+    ref = {"color0_u8": u1, "color1_u8": u0, "pad0": (320, 320), "pad1": (320, 320)}
+    model.forward_u8(ref)
+    for k in ("b_ids", "i_ids", "j_ids", "mconf", "mkpts0_f", "mkpts1_f"):
+        assert torch.equal(d_b[k], ref[k]), k
+    assert d_b["b_ids"].numel() > 100 and model.last_h2d_bytes == 2 * u0.numel()
+    with pytest.raises(RuntimeError, match="already been consumed"):
+        model.forward_u8({"staged": s_a})
+
+
 def test_corr_range_flag_falls_back_to_exact_sweeps():
     """csrc/corr_sweep.cu: a softmax sum outside the safe range of the fixed exponent reference raises the device flag and
     the forward repeats the coarse matching with the exact (online-max) sweeps.  Forced here by biasing the reference by
