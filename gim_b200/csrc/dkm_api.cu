@@ -115,6 +115,7 @@ int build_dkm(gimb_dkm* m, Ctx& ctx) {
     std::vector<uint32_t> sh;
     GIMB_TRY(m->ws.find(pre + ".emb_w", &r.emb_w, &sh));
     GIMB_TRY(m->ws.find(pre + ".emb_b", &r.emb_b));
+    GIMB_CHECK(!sh.empty() && sh[0] > 0, "weight blob: %s.emb_w has no shape", pre.c_str());
     r.emb = (int)sh[0];
     r.radius = rad[i]; r.feat = feat[i];
     r.cin = 2 * r.feat + r.emb + (r.radius ? (2 * r.radius + 1) * (2 * r.radius + 1) : 0);
@@ -127,7 +128,11 @@ int build_dkm(gimb_dkm* m, Ctx& ctx) {
       GIMB_TRY(m->ws.find(bp + ".dw_wt", &r.dw_wt[k]));
       GIMB_TRY(m->ws.find(bp + ".dw_sp", &r.dw_sp[k]));
       GIMB_TRY(m->ws.find(bp + ".dw_bp", &r.dw_bp[k]));
-      if (k == 0) { r.hidden = (int)dsh[0]; r.mult = r.hidden / r.cin; }
+      if (k == 0) {
+        GIMB_CHECK(!dsh.empty() && r.cin > 0, "weight blob: %s.dw_w has no shape", bp.c_str());
+        r.hidden = (int)dsh[0];
+        r.mult = r.hidden / r.cin;
+      }
       GIMB_TRY(m->ws.load_conv(ctx, bp + ".pw", true, &r.pw[k]));
     }
     GIMB_CHECK(r.hidden == r.cin * r.mult && r.pw[0].cin == r.hidden, "refiner %s: inconsistent channel counts", rs[i]);
@@ -575,10 +580,14 @@ static int dkm_run(gimb_dkm* h, const MatchArgs& a, void* workspace, size_t work
   ctx.sm_count = h->sm_count;
   ctx.dry = dry;
   ctx.arena.dry = dry;
-  ctx.arena.base = (char*)workspace;
-  ctx.arena.cap = workspace_bytes;
+  // like gimb_loftr_forward: the arena starts at the next kAlign boundary of whatever the caller passes
+  const uintptr_t base = ((uintptr_t)workspace + Arena::kAlign - 1) / Arena::kAlign * Arena::kAlign;
+  const size_t skew = base - (uintptr_t)workspace;
+  GIMB_CHECK(dry || workspace_bytes > skew, "gimb_dkm_match: workspace too small");
+  ctx.arena.base = (char*)base;
+  ctx.arena.cap = dry ? 0 : workspace_bytes - skew;
   int rc = match_impl(ctx, h, a);
-  if (need) *need = ctx.arena.peak + 4096;
+  if (need) *need = ctx.arena.peak + 4096 + Arena::kAlign;
   h->launches += ctx.launches;
   return rc;
 }

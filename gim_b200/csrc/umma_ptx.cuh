@@ -235,14 +235,14 @@ int get_encode(EncodeTiledFn* out) {
 // dims 1.. (rank-1 entries).
 // Encoded tensor maps are a pure function of (address, extents, strides, box, type): a forward re-creates the same ~1500
 // descriptors every call (same workspace layout for the same shapes), so they are cached per host thread.
-struct TMapKey {
-  uint64_t v[15];
+struct TMapKey {   // [0] address, [1] rank | type, [2..6] extents, [7..10] strides, [11..15] box
+  uint64_t v[16];
   bool operator==(const TMapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
 };
 struct TMapKeyHash {
   size_t operator()(const TMapKey& k) const {
     uint64_t h = 1469598103934665603ull;
-    for (int i = 0; i < 15; ++i) { h ^= k.v[i]; h *= 1099511628211ull; }
+    for (int i = 0; i < 16; ++i) { h ^= k.v[i]; h *= 1099511628211ull; }
     return (size_t)h;
   }
 };
@@ -254,8 +254,9 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, co
   memset(&key, 0, sizeof(key));
   key.v[0] = (uint64_t)(uintptr_t)ptr;
   key.v[1] = (uint64_t)rank | (f32 ? 1ull << 32 : 0ull);
-  for (int i = 0; i < rank; ++i) { key.v[2 + i] = dims[i]; key.v[10 + i] = box[i]; }
-  for (int i = 0; i + 1 < rank; ++i) key.v[6 + i] = strides_bytes[i];
+  GIMB_CHECK(rank >= 1 && rank <= 5, "tensor map: rank %d", rank);
+  for (int i = 0; i < rank; ++i) { key.v[2 + i] = dims[i]; key.v[11 + i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.v[7 + i] = strides_bytes[i];
   auto it = cache.find(key);
   if (it != cache.end()) {
     *m = it->second;
